@@ -1,0 +1,118 @@
+/*
+ * batch_prep.h — host-side preparation of one scoring batch (pure C++, no CUDA):
+ * validate the flat tree, convert it to the device layout, derive ring sizes from
+ * the configs and build the config-sorted work list.  Used by capi.cu and by the
+ * CPU build of the kernel under tests/emu.
+ */
+#ifndef REMY_BATCH_PREP_H
+#define REMY_BATCH_PREP_H
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "device_layout.h"
+
+namespace remy {
+
+inline uint32_t next_pow2(uint64_t v)
+{
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return (uint32_t)std::min<uint64_t>(p, 1u << 30);
+}
+
+struct PreparedTree {
+  std::vector<Bounds> bounds;     /* [n_nodes][NAX] */
+  std::vector<DevNodeMeta> meta;  /* [n_nodes] */
+  std::vector<DevLeaf> leaves;    /* [n_leaves] */
+  uint32_t axes_mask = 0;
+  size_t bytes() const { return bounds.size() * sizeof(Bounds) + meta.size() * sizeof(DevNodeMeta) + leaves.size() * sizeof(DevLeaf); }
+};
+
+/* Returns "" or a description of what is wrong with the tree. */
+inline std::string prepare_tree(const RemyFlatTree *tree, PreparedTree &out)
+{
+  if (!tree || !tree->nodes || !tree->leaves || tree->n_nodes == 0 || tree->n_leaves == 0) return "empty tree";
+  uint32_t mask = 0;
+  for (uint32_t i = 0; i < tree->n_nodes; i++) {
+    const RemyTreeNode &nd = tree->nodes[i];
+    mask |= nd.axis_mask & ((1u << NAX) - 1u);
+    if (nd.child_count) {
+      /* children must lie after their parent: the descent then always terminates */
+      if ((uint64_t)nd.child_begin + nd.child_count > tree->n_nodes || nd.child_begin <= i)
+        return "tree node " + std::to_string(i) + " has an invalid child range";
+    } else if (nd.leaf_index >= tree->n_leaves) {
+      return "tree node " + std::to_string(i) + " has an invalid leaf index";
+    }
+  }
+  out.axes_mask = mask;
+  out.bounds.resize((size_t)tree->n_nodes * NAX);
+  out.meta.resize(tree->n_nodes);
+  out.leaves.resize(tree->n_leaves);
+  for (uint32_t i = 0; i < tree->n_nodes; i++) {
+    const RemyTreeNode &nd = tree->nodes[i];
+    for (int a = 0; a < NAX; a++) {
+      Bounds b;
+      /* MemoryRange::contains only tests the node's own active axes
+       * (reference src/memoryrange.cc:52-58); widening the others lets the kernel
+       * test the union of axes for every node. */
+      if (nd.axis_mask & (1u << a)) { b.lo = nd.lower[a]; b.hi = nd.upper[a]; }
+      else { b.lo = -INFINITY; b.hi = INFINITY; }
+      out.bounds[(size_t)i * NAX + a] = b;
+    }
+    out.meta[i].first = nd.child_count ? nd.child_begin : nd.leaf_index;
+    out.meta[i].count = nd.child_count;
+  }
+  for (uint32_t i = 0; i < tree->n_leaves; i++) {
+    out.leaves[i].window_multiple = tree->leaves[i].window_multiple;
+    out.leaves[i].intersend = tree->leaves[i].intersend;
+    out.leaves[i].window_increment = tree->leaves[i].window_increment;
+    out.leaves[i].pad = 0;
+  }
+  return "";
+}
+
+struct BatchPlan {
+  uint32_t n_max = 1;       /* largest valid num_senders */
+  uint32_t link_cap = 1;    /* ring entries per slot (power of two) */
+  uint32_t delay_cap = 8;
+  std::vector<uint32_t> order; /* simulation ids, most expensive first, grouped by num_senders */
+};
+
+constexpr uint32_t LINK_CAP_FIRST_TRY = 4096; /* for limits above this (incl. "infinite"); grown on overflow */
+
+inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t n_cands)
+{
+  BatchPlan p;
+  uint64_t lim_max = 0; double bdp_max = 0; bool any_big = false;
+  for (uint32_t k = 0; k < n_cfgs; k++) {
+    const RemyNetConfig &c = cfgs[k];
+    if (c.num_senders >= 1 && c.num_senders <= REMY_MAX_SENDERS) p.n_max = std::max(p.n_max, c.num_senders);
+    if (c.buffer_size > LINK_CAP_FIRST_TRY) any_big = true; else lim_max = std::max<uint64_t>(lim_max, c.buffer_size);
+    const double bdp = c.link_ppt * c.delay;
+    if (c.link_ppt > 0 && c.delay >= 0 && std::isfinite(bdp)) bdp_max = std::max(bdp_max, bdp);
+  }
+  p.link_cap = next_pow2(std::max<uint64_t>(any_big ? LINK_CAP_FIRST_TRY : 1, std::max<uint64_t>(lim_max, 1)));
+  /* the delay line holds at most floor(delay * link_ppt) + 1 packets in flight plus the
+   * delivered-but-unread ones of the current tick */
+  p.delay_cap = next_pow2((uint64_t)std::min(bdp_max, 1048000.0) + 8);
+  const uint32_t n_sims = n_cands * n_cfgs;
+  p.order.resize(n_sims);
+  for (uint32_t i = 0; i < n_sims; i++) p.order[i] = i;
+  std::vector<double> cost(n_cfgs);
+  for (uint32_t k = 0; k < n_cfgs; k++) cost[k] = cfgs[k].link_ppt * cfgs[k].simulation_ticks;
+  /* instances sorted by config: same num_senders together (same loop trip counts in a
+   * warp), longest first (the tail of the batch is made of the shortest simulations) */
+  std::stable_sort(p.order.begin(), p.order.end(), [&](uint32_t x, uint32_t y) {
+    const uint32_t kx = x % n_cfgs, ky = y % n_cfgs;
+    if (cfgs[kx].num_senders != cfgs[ky].num_senders) return cfgs[kx].num_senders > cfgs[ky].num_senders;
+    if (cost[kx] != cost[ky]) return cost[kx] > cost[ky];
+    return kx < ky;
+  });
+  return p;
+}
+
+} // namespace remy
+#endif

@@ -1,0 +1,55 @@
+/*
+ * device_layout.h — data layout in HBM shared by the kernel (sim_kernel.cuh) and
+ * the host code that fills it (batch_prep.h, capi.cu).  Plain structs only.
+ */
+#ifndef REMY_DEVICE_LAYOUT_H
+#define REMY_DEVICE_LAYOUT_H
+
+#include <stdint.h>
+#include "../../include/remy_b200.h"
+
+#if defined(__CUDACC__) || defined(REMY_HOST_EMU)
+#define REMY_ALIGN(n) __align__(n)
+#else
+#define REMY_ALIGN(n) alignas(n)
+#endif
+
+namespace remy {
+
+constexpr int NAX = REMY_NUM_AXES;
+
+/* Per-(slot, sender) state that is touched only when that sender gets an ack,
+ * transmits or switches: one 128-byte line in HBM/L2. */
+struct REMY_ALIGN(16) SenderCold {
+  double mem[NAX];          /* Memory::field(0..5) (reference src/memory.hh:97) */
+  double last_tick_sent;    /* Memory::_last_tick_sent */
+  double last_tick_received;
+  double min_rtt;
+  double total_delay;       /* Utility::_total_delay */
+  double last_send_time;    /* Rat::_last_send_time */
+  double intersend;         /* Rat::_intersend_time */
+  double next_switch;       /* SwitchedSender::next_switch_tick */
+  uint32_t packets_sent;    /* Rat::_packets_sent */
+  int32_t largest_ack;      /* Rat::_largest_ack */
+  int32_t window;           /* Rat::_the_window */
+  uint32_t u_received;      /* Utility::_packets_received */
+  uint32_t leaf;            /* leaf returned by the sender's latest lookup */
+  uint32_t pad;
+};
+static_assert(sizeof(SenderCold) == 128, "SenderCold must be one 128-byte line");
+
+/* Link::_buffer entry and Delay::_queue entry (reference src/link.hh:15, src/delay.hh:16);
+ * flow_id and tick_received are not stored: the first is dead on the Rat path, the second
+ * is the tick at which the entry is consumed. */
+struct REMY_ALIGN(16) LinkEnt { double tick_sent; uint32_t seq; uint32_t src; };
+struct REMY_ALIGN(16) DelayEnt { double release; double tick_sent; uint32_t seq; uint32_t src; uint32_t pad[2]; };
+static_assert(sizeof(LinkEnt) == 16 && sizeof(DelayEnt) == 32, "ring entry sizes");
+
+/* Device copy of the tree: bounds[node][axis] = (lower, upper) with axes a node does not
+ * test widened to (-inf, +inf); meta[node] = (child_begin or leaf_index, child_count). */
+struct REMY_ALIGN(16) Bounds { double lo, hi; };
+struct DevNodeMeta { uint32_t first; uint32_t count; };
+struct REMY_ALIGN(8) DevLeaf { double window_multiple; double intersend; int32_t window_increment; uint32_t pad; };
+
+} // namespace remy
+#endif

@@ -1,0 +1,600 @@
+/*
+ * sim_kernel.cuh — the sm_100a simulation kernel: one thread per (candidate,
+ * config) simulation, persistent blocks pulling work from a cost-sorted list.
+ *
+ * What it computes is exactly what the reference computes for
+ *   Evaluator<WhiskerTree>::score(tree, seed, {config}, false, ticks)
+ * (reference src/evaluator.cc:77-103 -> src/network.cc:63-85), but the loop is
+ * re-organised for a GPU thread instead of translated:
+ *
+ *   reference (per event tick)                    this kernel
+ *   ---------------------------------------------------------------------------
+ *   2x count_active_senders O(n)                  popc of a 32-bit on-mask
+ *   switch_senders: n switcher() calls            one compare against a cached
+ *     (sendergang.cc:39-45,89-106)                min-switch time; O(n) scan only
+ *                                                 on the rare ticks that switch
+ *   std::shuffle of a heap-allocated index        PRNG advanced by the exact n/2
+ *     vector every tick (sendergang.cc:75-82)     draws (rejections honoured); the
+ *                                                 permutation is only materialised
+ *                                                 when >= 2 senders transmit in the
+ *                                                 same tick (the only case in which
+ *                                                 the order is observable)
+ *   n TimeSwitchedSender::tick calls              acks taken from the delay ring's
+ *     (sendergang.cc:190-205)                     "delivered" window; sends only for
+ *                                                 senders whose pacing deadline is due
+ *   tick_share += dt/k per sending sender         same additions, same order per
+ *     (sendergang.cc:163-173, utility.hh:19)      sender (bit-exact), dt/k hoisted
+ *   SenderGang::next_event_time O(n) + Rat O(1)   min(min_switch, min of due times
+ *     (sendergang.cc:326-347, rat.cc:50-62)       of window-open senders)
+ *   std::deque<Packet> x3, vector<vector<Packet>> two per-slot rings in HBM; the
+ *     (link.hh, delay.hh, receiver.hh)            Receiver mailbox is a window of the
+ *                                                 delay ring, never copied
+ *
+ * Every floating-point expression that feeds control flow keeps the
+ * reference's association and is compiled without FMA contraction
+ * (--fmad=false plus explicit _rn intrinsics where it matters).
+ */
+#ifndef REMY_SIM_KERNEL_CUH
+#define REMY_SIM_KERNEL_CUH
+
+#include <stdint.h>
+#include <float.h>
+#ifdef REMY_HOST_EMU
+/* tests/emu builds this header with g++ to check the restructured event loop
+ * against the oracle on machines without a GPU.  Test infrastructure only: the
+ * shipped library is always the nvcc build. */
+#include "host_emu.h"
+#define REMY_NOINLINE __attribute__((noinline))
+#else
+#include <cuda_runtime.h>
+#define REMY_NOINLINE __noinline__
+#endif
+#include "../../include/remy_b200.h"
+#include "exact_log.h"
+#include "device_layout.h"
+
+namespace remy {
+
+constexpr uint32_t LCG_M = 2147483647u;
+
+struct KernelArgs {
+  /* tree (global copies; staged into shared memory when it fits) */
+  const Bounds *bounds;        /* [n_nodes][NAX] */
+  const DevNodeMeta *meta;     /* [n_nodes] */
+  const DevLeaf *leaves;       /* [n_leaves] */
+  uint32_t n_nodes, n_leaves, axes_mask, tree_in_smem;
+  /* batch */
+  const RemyLeafOverride *cands; /* [n_cands] or nullptr */
+  const RemyNetConfig *cfgs;     /* [n_cfgs] */
+  const uint32_t *seeds;         /* [n_cfgs] */
+  const uint32_t *order;         /* [n_work] simulation ids, cost-sorted */
+  uint32_t n_cfgs, n_work;
+  uint32_t *work_counter;
+  /* per-slot scratch */
+  SenderCold *cold;   uint32_t n_max;      /* [slots][n_max] */
+  LinkEnt *link_ring; uint32_t link_cap;   /* [slots][link_cap], power of two */
+  DelayEnt *delay_ring; uint32_t delay_cap;/* [slots][delay_cap], power of two */
+  uint32_t *slot_counts;                   /* [slots][n_leaves] when counting uses */
+  /* outputs */
+  RemySimResult *out_sims;                 /* [n_sims] */
+  RemySenderResult *out_senders; uint32_t sender_stride; /* optional */
+  uint32_t *out_use_counts;                /* [n_cands][n_leaves], optional */
+};
+
+/* ---------------------------------------------------------------- PRNG ---- */
+/* minstd_rand0 step (bits/random.h:1592, 368-372): 16807 x mod (2^31-1) via the
+ * Mersenne fold (2^31 == 1 mod m). */
+__device__ __forceinline__ uint32_t lcg_next(uint32_t x)
+{
+  const uint64_t p = (uint64_t)x * 16807u;
+  uint32_t r = (uint32_t)(p & 0x7fffffffu) + (uint32_t)(p >> 31);
+  return r >= LCG_M ? r - LCG_M : r;
+}
+__device__ __forceinline__ uint32_t lcg_mul(uint32_t x, uint32_t a) /* a x mod m, a,x < 2^31 */
+{
+  const uint64_t p = (uint64_t)x * a;
+  uint64_t r = (p & 0x7fffffffu) + (p >> 31);          /* < 2^32 */
+  r = (r & 0x7fffffffu) + (r >> 31);
+  return (uint32_t)(r >= LCG_M ? r - LCG_M : r);
+}
+
+/* std::generate_canonical<double,53> for this engine (bits/random.tcc:3349-3383). */
+__device__ __forceinline__ double canonical(uint32_t &x)
+{
+  x = lcg_next(x);
+  const double a = (double)(x - 1u);
+  x = lcg_next(x);
+  const double b = __dmul_rn((double)(x - 1u), 2147483646.0);
+  double ret = __ddiv_rn(__dadd_rn(a, b), 0x1.fffffffp+61);
+  if (ret >= 1.0) ret = 0x1.fffffffffffffp-1; /* nextafter(1, 0) */
+  return ret;
+}
+
+/* Exponential::sample (src/exponential.hh:22; bits/random.h:4898-4905). */
+__device__ REMY_NOINLINE double exp_sample(uint32_t &x, double rate)
+{
+  const double u = canonical(x);
+  return __ddiv_rn(-remy_exact_log(__dsub_rn(1.0, u)), rate);
+}
+
+/* uniform_int_distribution{0,u}, fallback branch (bits/uniform_int_dist.h:333-339). */
+__device__ __forceinline__ uint32_t uniform_int(uint32_t &x, uint32_t u)
+{
+  const uint32_t uerange = u + 1u;
+  const uint32_t scaling = 2147483645u / uerange, past = uerange * scaling;
+  uint32_t ret;
+  do { x = lcg_next(x); ret = x - 1u; } while (ret >= past);
+  return ret / scaling;
+}
+
+/* The largest remainder 2147483645 mod ((i+1)(i+2)) over all shuffle ranges with
+ * n <= 32 is < 1122, so a draw below this bound can never be rejected. */
+constexpr uint32_t SHUFFLE_SAFE = 2147483645u - 1122u;
+
+/* Advance the PRNG by exactly the draws std::shuffle makes for n elements
+ * (bits/stl_algo.h:3742-3805) without building the permutation. */
+__device__ __forceinline__ uint32_t shuffle_skip(uint32_t x, uint32_t n)
+{
+  const uint32_t x0 = x;
+  const uint32_t draws = n >> 1;
+  uint32_t mx = 0;
+  for (uint32_t j = 0; j < draws; j++) { x = lcg_next(x); mx = max(mx, x); }
+  if (mx - 1u < SHUFFLE_SAFE) return x;
+  /* a draw landed within ~1e-6 of the top of the range: redo exactly */
+  x = x0;
+  uint32_t i = 1;
+  if ((n & 1u) == 0) { (void)uniform_int(x, 1); i = 2; }
+  for (; i < n; i += 2) (void)uniform_int(x, (i + 1) * (i + 2) - 1);
+  return x;
+}
+
+/* Build the permutation (only when two senders transmit in one tick). */
+__device__ REMY_NOINLINE void shuffle_materialise(uint32_t x, uint32_t n, uint8_t *idx)
+{
+  for (uint32_t i = 0; i < n; i++) idx[i] = (uint8_t)i;
+  uint32_t i = 1;
+  uint8_t t;
+  if ((n & 1u) == 0) {
+    const uint32_t d = uniform_int(x, 1);
+    t = idx[1]; idx[1] = idx[d]; idx[d] = t;
+    i = 2;
+  }
+  for (; i < n; i += 2) {
+    const uint32_t b1 = i + 2;
+    const uint32_t v = uniform_int(x, (i + 1) * b1 - 1);
+    const uint32_t p0 = v / b1, p1 = v % b1;
+    t = idx[i]; idx[i] = idx[p0]; idx[p0] = t;
+    t = idx[i + 1]; idx[i + 1] = idx[p1]; idx[p1] = t;
+  }
+}
+
+/* ------------------------------------------------------------- whiskers --- */
+struct TreeView {
+  const Bounds *bounds;  const DevNodeMeta *meta; const DevLeaf *leaves;
+  uint32_t axes_mask;
+};
+
+__device__ __forceinline__ bool node_contains(const TreeView &T, uint32_t node, const double *m)
+{
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < NAX; a++) {
+    if (T.axes_mask & (1u << a)) {
+      const Bounds b = T.bounds[node * NAX + a];
+      ok = ok && (m[a] >= b.lo) && (m[a] < b.hi);
+    }
+  }
+  return ok;
+}
+
+/* WhiskerTree::whisker (src/whiskertree.cc:62-82): first-match descent.
+ * Returns the leaf index, or sets err and returns 0xFFFFFFFF. */
+__device__ __forceinline__ uint32_t find_leaf(const TreeView &T, const double *m, uint32_t &err)
+{
+  if (!node_contains(T, 0, m)) { err |= REMY_ERR_NO_WHISKER; return 0xFFFFFFFFu; }
+  uint32_t cur = 0;
+  for (;;) {
+    const DevNodeMeta md = T.meta[cur];
+    if (md.count == 0) return md.first;
+    uint32_t next = 0xFFFFFFFFu;
+    for (uint32_t c = 0; c < md.count; c++) {
+      if (node_contains(T, md.first + c, m)) { next = md.first + c; break; }
+    }
+    if (next == 0xFFFFFFFFu) { err |= REMY_ERR_NO_CHILD; return 0xFFFFFFFFu; }
+    cur = next;
+  }
+}
+
+/* Whisker::window (src/whisker.hh:25), with the x86-64 cvttsd2si result for
+ * out-of-range values that the reference's build produces. */
+__device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int32_t incr)
+{
+  const double v = __dadd_rn(__dmul_rn((double)(uint32_t)prev, mult), (double)incr);
+  int32_t iv = __double2int_rz(v);
+  if (iv == 0x7fffffff && v >= 2147483648.0) iv = (int32_t)0x80000000;
+  return min(max(0, iv), 1000000);
+}
+
+/* ------------------------------------------------------------- the sim ---- */
+template <bool COUNT>
+__device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
+                        double *hot_share, double *hot_send, /* [s * blockDim.x] strided */
+                        SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
+{
+  const uint32_t HS = blockDim.x; /* stride of the shared-memory hot arrays */
+  const uint32_t cand = sim / A.n_cfgs, cfg_i = sim - cand * A.n_cfgs;
+  const RemyNetConfig cfg = A.cfgs[cfg_i];
+  RemySimResult res;
+  res.utility = 0; res.last_tick = 0; res.event_ticks = 0; res.packets_sent = 0; res.packets_received = 0;
+  res.link_queued = 0; res.delay_inflight = 0; res.prng_state = 0; res.error = 0;
+
+  const uint32_t n = cfg.num_senders;
+  if (n == 0 || n > A.n_max || n > REMY_MAX_SENDERS || !(cfg.simulation_ticks > 0) || !(cfg.link_ppt > 0)) {
+    res.error = REMY_ERR_BAD_CONFIG;
+    A.out_sims[sim] = res;
+    if (A.out_senders) {
+      RemySenderResult z; z.tick_share_sending = 0; z.total_delay = 0; z.packets_received = 0; z.packets_sent = 0;
+      for (uint32_t s = 0; s < A.sender_stride; s++) A.out_senders[(size_t)sim * A.sender_stride + s] = z;
+    }
+    return;
+  }
+
+  /* candidate override (WhiskerTree::replace, src/whiskertree.cc:137-157) */
+  uint32_t ov_leaf = REMY_NO_OVERRIDE;
+  if (A.cands) ov_leaf = A.cands[cand].leaf_index;
+
+  uint32_t prng = A.seeds[cfg_i] % LCG_M; /* bits/random.tcc:116-126 */
+  if (prng == 0) prng = 1;
+  uint32_t err = 0;
+
+  const double duration = cfg.simulation_ticks;
+  const double start_rate = __ddiv_rn(1.0, cfg.mean_off_duration); /* sendergang.cc:18-19 */
+  const double stop_rate = __ddiv_rn(1.0, cfg.mean_on_duration);
+  const double service = __ddiv_rn(1.0, cfg.link_ppt);            /* link.hh:24 */
+  const double delay = cfg.delay;
+  const double loss_p = cfg.stochastic_loss_rate;
+  const uint32_t limit = cfg.buffer_size;
+  const uint32_t lmask = A.link_cap - 1, dmask = A.delay_cap - 1;
+
+  /* SenderGang ctor (sendergang.cc:9-26), Rat ctor (rat.cc:8-20) */
+  double min_switch = DBL_MAX;
+  for (uint32_t s = 0; s < n; s++) {
+    SenderCold c;
+#pragma unroll
+    for (int a = 0; a < NAX; a++) c.mem[a] = 0;
+    c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0; c.total_delay = 0;
+    c.last_send_time = 0; c.intersend = 0;
+    c.next_switch = exp_sample(prng, start_rate);
+    c.packets_sent = 0; c.largest_ack = -1; c.window = 0; c.u_received = 0; c.leaf = 0; c.pad = 0;
+    cold[s] = c;
+    min_switch = fmin(min_switch, c.next_switch);
+    hot_share[s * HS] = 0.0;
+    hot_send[s * HS] = DBL_MAX;
+  }
+  if (COUNT) for (uint32_t l = 0; l < A.n_leaves; l++) cnt[l] = 0;
+
+  double t = 0.0, t_prev = 0.0;
+  uint32_t on_mask = 0, open_mask = 0, zero_mask = 0;
+  double next_send = DBL_MAX;          /* min of hot_send over open senders */
+  bool pending = false;                /* Link::_pending_packet non-empty */
+  double pend_release = 0, pend_sent = 0; uint32_t pend_seq = 0, pend_src = 0;
+  uint32_t lhead = 0, ltail = 0;       /* Link::_buffer ring */
+  uint32_t dcons = 0, ddeliv = 0, dtail = 0; /* delay ring: [dcons,ddeliv) = Receiver mailbox, [ddeliv,dtail) in flight */
+  double dhead_release = DBL_MAX;
+  uint64_t iters = 0;
+
+  while (t < duration) {
+    /* ---- next event (network.cc:75-78) ---- */
+    double tn = fmax(t, fmin(min_switch, next_send)); /* SenderGang::next_event_time */
+    if (pending) tn = fmin(tn, pend_release);           /* Link::next_event_time */
+    if (ddeliv != dtail) tn = fmin(tn, dhead_release);  /* Delay::next_event_time */
+    if (dcons != ddeliv) tn = fmin(tn, t);              /* Receiver::next_event_time */
+    t = tn;
+    if (t > duration) break;
+    iters++;
+    const bool advanced = t > t_prev;
+
+    /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
+    uint32_t newly_on = 0;
+    if (min_switch <= t) {
+      const uint32_t k0 = __popc(on_mask);
+      double ms = DBL_MAX;
+      for (uint32_t s = 0; s < n && !err; s++) {
+        double nsw = cold[s].next_switch;
+        if (nsw <= t) {
+          if (nsw != t) err |= REMY_ERR_ASSERT;
+          SenderCold c = cold[s];
+          bool sending = (on_mask >> s) & 1u;
+          double itick = t_prev;       /* SwitchedSender::internal_tick of a sender that was on */
+          double share = hot_share[s * HS];
+          do {
+            if (sending) {             /* switch_off (sendergang.cc:151-161) */
+              if (t > itick) { share = __dadd_rn(share, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
+              sending = false;
+            } else {                   /* switch_on -> Rat::reset (rat.cc:34-48) */
+              sending = true;
+#pragma unroll
+              for (int a = 0; a < NAX; a++) c.mem[a] = 0;
+              c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0;
+              c.last_send_time = 0;
+              c.largest_ack = (int32_t)(c.packets_sent - 1u);
+              const uint32_t leaf = find_leaf(T, c.mem, err);
+              if (err) break;
+              if (COUNT) cnt[leaf]++;
+              DevLeaf w = T.leaves[leaf];
+              if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
+              c.window = whisker_window(0, w.window_multiple, w.window_increment);
+              c.intersend = w.intersend;
+              c.leaf = leaf;
+              itick = t;
+            }
+            nsw = __dadd_rn(nsw, exp_sample(prng, sending ? stop_rate : start_rate));
+          } while (nsw <= t);
+          c.next_switch = nsw;
+          cold[s] = c;
+          hot_share[s * HS] = share;
+          const uint32_t bit = 1u << s;
+          if (sending) {
+            on_mask |= bit;
+            if (itick == t) newly_on |= bit;
+            const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
+            hot_send[s * HS] = open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX;
+            open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
+            if (COUNT) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+          } else {
+            on_mask &= ~bit; open_mask &= ~bit;
+            hot_send[s * HS] = DBL_MAX;
+            if (COUNT) zero_mask &= ~bit;
+          }
+        }
+        ms = fmin(ms, nsw);
+      }
+      min_switch = ms;
+      if (err) break;
+    }
+    const uint32_t k1 = __popc(on_mask);
+
+    /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
+    const uint32_t prng_before_shuffle = prng;
+    prng = shuffle_skip(prng, n);
+
+    /* ---- 3. receive_feedback for every mailbox (sendergang.cc:175-188) ---- */
+    if (dcons != ddeliv) {
+      uint32_t done = 0;
+      for (uint32_t i = dcons; i != ddeliv && !err; i++) {
+        const uint32_t s = dring[i & dmask].src;
+        if ((done >> s) & 1u) continue;
+        done |= 1u << s;
+        SenderCold c = cold[s];
+        const int32_t old_ack = c.largest_ack;
+        int32_t last_seq = 0;
+        for (uint32_t j = i; j != ddeliv; j++) {
+          const DelayEnt e = dring[j & dmask];
+          if (e.src != s) continue;
+          /* Utility::packets_received (utility.hh:20-27) */
+          const double rtt = __dsub_rn(t, e.tick_sent);
+          c.u_received++;
+          c.total_delay = __dadd_rn(c.total_delay, rtt);
+          /* Memory::packets_received (memory.cc:31-80) */
+          int32_t outstanding = 1;
+          if ((int64_t)e.seq > (int64_t)old_ack) outstanding = (int32_t)((int64_t)e.seq - (int64_t)old_ack);
+          if (c.min_rtt <= 0) c.min_rtt = rtt;
+          if (c.last_tick_sent == 0 || c.last_tick_received == 0) {
+            c.last_tick_sent = e.tick_sent; c.last_tick_received = t; c.min_rtt = rtt;
+          } else {
+            const double ds = __dsub_rn(e.tick_sent, c.last_tick_sent);
+            const double dr = __dsub_rn(t, c.last_tick_received);
+            c.mem[0] = __dadd_rn(__dmul_rn(0.875, c.mem[0]), __dmul_rn(0.125, ds));
+            c.mem[1] = __dadd_rn(__dmul_rn(0.875, c.mem[1]), __dmul_rn(0.125, dr));
+            c.mem[3] = __dadd_rn(__dmul_rn(0.99609375, c.mem[3]), __dmul_rn(0.00390625, dr));
+            c.last_tick_sent = e.tick_sent; c.last_tick_received = t;
+            c.min_rtt = (rtt < c.min_rtt) ? rtt : c.min_rtt;
+            c.mem[2] = __ddiv_rn(rtt, c.min_rtt);
+            c.mem[4] = __dsub_rn(rtt, c.min_rtt);
+            if (!(c.mem[2] >= 1.0) || !(c.mem[4] >= 0)) err |= REMY_ERR_ASSERT;
+            c.mem[5] = __dmul_rn(c.mem[1], (double)outstanding);
+          }
+          last_seq = (int32_t)e.seq;
+        }
+        /* Rat::packets_received (rat.cc:22-32) */
+        c.largest_ack = max(last_seq, old_ack);
+        const uint32_t leaf = find_leaf(T, c.mem, err);
+        if (err) break;
+        if (COUNT) cnt[leaf]++;
+        DevLeaf w = T.leaves[leaf];
+        if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
+        c.window = whisker_window(c.window, w.window_multiple, w.window_increment);
+        c.intersend = w.intersend;
+        c.leaf = leaf;
+        cold[s] = c;
+        const uint32_t bit = 1u << s;
+        if (on_mask & bit) {
+          const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
+          hot_send[s * HS] = open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX;
+          open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
+          if (COUNT) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+        }
+      }
+      dcons = ddeliv;
+      if (err) break;
+    }
+
+    /* Rat::send's lookup when the window is 0 (rat-templates.cc:13-18): the
+     * memory has not changed since the sender's last lookup, so it returns the
+     * same leaf and the same window/intersend; only the use count moves. */
+    if (COUNT) {
+      uint32_t zm = zero_mask & on_mask;
+      while (zm) { const uint32_t s = __ffs(zm) - 1; zm &= zm - 1; cnt[cold[s].leaf]++; }
+    }
+
+    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34) ---- */
+    {
+      uint32_t ready = 0;
+      double ns = DBL_MAX;
+      uint32_t om = open_mask;
+      while (om) {
+        const uint32_t s = __ffs(om) - 1; om &= om - 1;
+        const double st = hot_send[s * HS];
+        if (st <= t) ready |= 1u << s; else ns = fmin(ns, st);
+      }
+      if (ready) {
+        uint8_t perm[REMY_MAX_SENDERS];
+        const bool ordered = (ready & (ready - 1)) != 0;
+        if (ordered) shuffle_materialise(prng_before_shuffle, n, perm);
+        uint32_t left = ready;
+        for (uint32_t i = 0; left; i++) {
+          uint32_t s;
+          if (ordered) { s = perm[i]; if (!((left >> s) & 1u)) continue; }
+          else s = __ffs(left) - 1;
+          left &= ~(1u << s);
+          SenderCold *c = &cold[s];
+          const uint32_t seq = c->packets_sent;
+          const int32_t lim = c->largest_ack + 1 + c->window;
+          const double isend = c->intersend;
+          c->packets_sent = seq + 1;
+          c->last_send_time = t;
+          /* Link::accept (link.hh:26-34) */
+          if (!pending) {
+            pending = true; pend_release = __dadd_rn(t, service); pend_sent = t; pend_seq = seq; pend_src = s;
+          } else if (limit && (ltail - lhead) < limit) {
+            if (ltail - lhead >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
+            LinkEnt e; e.tick_sent = t; e.seq = seq; e.src = s;
+            lring[ltail & lmask] = e; ltail++;
+          }
+          const bool open = (int32_t)(seq + 1) < lim;
+          const double st = open ? __dadd_rn(t, isend) : DBL_MAX;
+          hot_send[s * HS] = st;
+          if (!open) open_mask &= ~(1u << s);
+          ns = fmin(ns, st);
+        }
+        if (err) break;
+      }
+      next_send = ns;
+    }
+
+    /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) ---- */
+    if (advanced) {
+      uint32_t am = on_mask & ~newly_on;
+      if (am) {
+        const double inc = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
+        while (am) {
+          const uint32_t s = __ffs(am) - 1; am &= am - 1;
+          hot_share[s * HS] = __dadd_rn(hot_share[s * HS], inc);
+        }
+      }
+    }
+    t_prev = t;
+
+    /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
+    if (pending && pend_release <= t) {
+      if (pend_release != t) err |= REMY_ERR_ASSERT;
+      bool lost;
+      if (loss_p > 0.0) lost = canonical(prng) < loss_p;      /* bernoulli (bits/random.h:3739-3750) */
+      else { prng = lcg_mul(prng, 282475249u); lost = false; } /* two draws, 16807^2 */
+      if (!lost) {
+        if (dtail - dcons >= A.delay_cap) { err |= REMY_ERR_DELAY_OVERFLOW; break; }
+        DelayEnt e; e.release = __dadd_rn(t, delay); e.tick_sent = pend_sent; e.seq = pend_seq; e.src = pend_src; e.pad[0] = 0; e.pad[1] = 0;
+        dring[dtail & dmask] = e;
+        if (ddeliv == dtail) dhead_release = e.release;
+        dtail++;
+      }
+      pending = false;
+    }
+    if (!pending && lhead != ltail) {
+      const LinkEnt e = lring[lhead & lmask]; lhead++;
+      pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
+    }
+    /* ---- 7. Delay::tick (delay.hh:53-63) -> Receiver::accept ---- */
+    while (ddeliv != dtail && dhead_release <= t) {
+      if (dhead_release != t) err |= REMY_ERR_ASSERT;
+      ddeliv++;
+      if (ddeliv != dtail) dhead_release = dring[ddeliv & dmask].release;
+    }
+  }
+
+  /* ---- results: Utility::utility (utility.hh:46-60), SenderGang::utility (sendergang.cc:280-293) ---- */
+  double total = 0.0;
+  uint64_t sent = 0, recv = 0;
+  for (uint32_t s = 0; s < n; s++) {
+    const SenderCold c = cold[s];
+    const double share = hot_share[s * HS];
+    double u;
+    if (share == 0) u = 0.0;
+    else if (c.u_received == 0) u = -2147483647.0;
+    else {
+      const double tput = __ddiv_rn((double)c.u_received, share);
+      const double del = __ddiv_rn(c.total_delay, (double)c.u_received);
+      u = __dsub_rn(log2(tput), log2(__ddiv_rn(del, 100.0)));
+    }
+    total = __dadd_rn(total, u);
+    sent += c.packets_sent; recv += c.u_received;
+    if (A.out_senders && s < A.sender_stride) {
+      RemySenderResult r; r.tick_share_sending = share; r.total_delay = c.total_delay;
+      r.packets_received = c.u_received; r.packets_sent = c.packets_sent;
+      A.out_senders[(size_t)sim * A.sender_stride + s] = r;
+    }
+  }
+  if (A.out_senders) {
+    RemySenderResult z; z.tick_share_sending = 0; z.total_delay = 0; z.packets_received = 0; z.packets_sent = 0;
+    for (uint32_t s = n; s < A.sender_stride; s++) A.out_senders[(size_t)sim * A.sender_stride + s] = z;
+  }
+  res.utility = __ddiv_rn(total, (double)n);
+  res.last_tick = t;
+  res.event_ticks = iters;
+  res.packets_sent = sent; res.packets_received = recv;
+  res.link_queued = (ltail - lhead) + (pending ? 1u : 0u);
+  res.delay_inflight = dtail - dcons;
+  res.prng_state = prng;
+  res.error = err;
+  A.out_sims[sim] = res;
+  if (COUNT && A.out_use_counts && !(err & (REMY_ERR_LINK_OVERFLOW | REMY_ERR_DELAY_OVERFLOW))) {
+    /* (an overflowed simulation is re-run by the host with larger rings) */
+    for (uint32_t l = 0; l < A.n_leaves; l++) {
+      const uint32_t v = cnt[l];
+      if (v) atomicAdd(&A.out_use_counts[(size_t)cand * A.n_leaves + l], v);
+    }
+  }
+}
+
+constexpr int SIM_BLOCK = 128;
+
+#ifndef REMY_HOST_EMU
+
+template <bool COUNT>
+__global__ void __launch_bounds__(SIM_BLOCK) remy_sim_kernel(const KernelArgs A)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  /* layout: [hot_share: n_max*B doubles][hot_send: n_max*B doubles][tree, if staged] */
+  double *hot_share = reinterpret_cast<double *>(smem) + threadIdx.x;
+  double *hot_send = hot_share + (size_t)A.n_max * blockDim.x;
+  TreeView T;
+  T.axes_mask = A.axes_mask;
+  if (A.tree_in_smem) {
+    unsigned char *p = smem + (size_t)2 * A.n_max * blockDim.x * sizeof(double);
+    Bounds *sb = reinterpret_cast<Bounds *>(p);
+    DevLeaf *sl = reinterpret_cast<DevLeaf *>(sb + (size_t)A.n_nodes * NAX);
+    DevNodeMeta *sm = reinterpret_cast<DevNodeMeta *>(sl + A.n_leaves);
+    for (uint32_t i = threadIdx.x; i < A.n_nodes * NAX; i += blockDim.x) sb[i] = A.bounds[i];
+    for (uint32_t i = threadIdx.x; i < A.n_leaves; i += blockDim.x) sl[i] = A.leaves[i];
+    for (uint32_t i = threadIdx.x; i < A.n_nodes; i += blockDim.x) sm[i] = A.meta[i];
+    __syncthreads();
+    T.bounds = sb; T.leaves = sl; T.meta = sm;
+  } else {
+    T.bounds = A.bounds; T.leaves = A.leaves; T.meta = A.meta;
+  }
+  const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  SenderCold *cold = A.cold + slot * A.n_max;
+  LinkEnt *lring = A.link_ring + slot * A.link_cap;
+  DelayEnt *dring = A.delay_ring + slot * A.delay_cap;
+  uint32_t *cnt = COUNT ? A.slot_counts + slot * A.n_leaves : nullptr;
+  for (;;) {
+    const uint32_t w = atomicAdd(A.work_counter, 1u);
+    if (w >= A.n_work) break;
+    run_sim<COUNT>(A, T, A.order[w], hot_share, hot_send, cold, lring, dring, cnt);
+  }
+}
+
+#endif /* !REMY_HOST_EMU */
+
+} // namespace remy
+#endif

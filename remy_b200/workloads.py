@@ -1,0 +1,73 @@
+"""Synthetic workloads of the shapes BASELINE.json names (host logic, numpy only)."""
+import numpy as np
+
+from . import abi
+
+
+def config_range_points(low, high, incr):
+    """The reference's `for (x = low; x <= high; x += incr)` loops with the isOne()
+    early break (src/evaluator.cc:16-37, src/configrange.hh:30-33)."""
+    out = []
+    x = low
+    while x <= high:
+        out.append(x)
+        if low == high or incr == 0:
+            break
+        x += incr
+    return out
+
+
+def default_config_range(ticks=1e6, link=(1.0, 2.0, 0.25), rtt=(100.0, 200.0, 25.0), nsrc=(1, 32, 1),
+                         on=5000.0, off=5000.0, buffer_size=abi.BUFFER_INFINITE, loss=0.0):
+    """BASELINE config 2: link 1..2 ppt step 0.25, rtt 100..200 step 25,
+    nsrc 1..32, on = off = 5000 ms, infinite buffer, no loss -> 800 NetConfigs, in the
+    nesting order of Evaluator::Evaluator (link outermost, then rtt, then senders)."""
+    rows = []
+    for l in config_range_points(*link):
+        for r in config_range_points(*rtt):
+            for n in config_range_points(*nsrc):
+                rows.append(dict(link_ppt=l, delay=r, num_senders=int(n), mean_on_duration=on,
+                                 mean_off_duration=off, buffer_size=buffer_size,
+                                 stochastic_loss_rate=loss, simulation_ticks=ticks))
+    return abi.make_configs(rows)
+
+
+def seeds_for(evaluator_seed, n):
+    """Per-config seeds: the first n outputs of minstd_rand0(evaluator_seed) — the batched
+    evaluator's replacement for the single chained PRNG of src/evaluator.cc:84."""
+    m = 2147483647
+    x = evaluator_seed % m or 1
+    out = np.empty(n, dtype=np.uint32)
+    for i in range(n):
+        x = (x * 16807) % m
+        out[i] = x
+    return out
+
+
+def candidate_grid(leaf_index, base=(1, 1.0, 3.0), n=343):
+    """<= 343 single-leaf replacements shaped like Whisker::next_generation
+    (src/whisker.cc:46-81, src/action.hh:62-91) around `base` = (increment, multiple, intersend)."""
+    def alts(v, lo, hi, mn, mx, mul, integer):
+        out = [v]
+        c = mn
+        while c <= mx:
+            for s in (1, -1):
+                w = v + s * c
+                if integer and w < 0:
+                    continue
+                if lo <= w <= hi:
+                    out.append(w)
+            c *= mul
+        return out
+    incs = alts(base[0], 0, 256, 1, 32, 4, True)
+    muls = alts(base[1], 0.0, 1.0, 0.01, 0.5, 4, False)
+    ints = alts(base[2], 0.25, 3.0, 0.05, 1.0, 4, False)
+    cands = []
+    for i in incs:
+        for m in muls:
+            for s in ints:
+                cands.append((int(10000 * m) / 10000.0, int(10000 * s) / 10000.0, int(i), leaf_index))
+    arr = np.zeros(min(n, len(cands)), dtype=abi.leaf_override_dtype)
+    for k in range(len(arr)):
+        arr[k] = cands[k]
+    return arr

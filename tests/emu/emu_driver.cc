@@ -1,0 +1,57 @@
+/*
+ * emu_driver.cc — runs the kernel's run_sim<> (compiled for the host through
+ * host_emu.h) over a batch, with the same batch preparation as capi.cu.
+ * TEST INFRASTRUCTURE: checks the kernel's restructured loop without a GPU.
+ */
+#define REMY_HOST_EMU 1
+#include "host_emu.h"
+#include "../../remy_b200/csrc/sim_kernel.cuh"
+#include "../../remy_b200/csrc/batch_prep.h"
+
+#include <vector>
+#include <string>
+
+using namespace remy;
+
+extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
+                                    const RemyLeafOverride *cands, uint32_t n_cands,
+                                    const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                    uint32_t sender_stride,
+                                    RemySimResult *out_sims, RemySenderResult *out_senders,
+                                    uint32_t *out_use_counts, uint32_t link_cap_override)
+{
+  PreparedTree pt;
+  if (!prepare_tree(tree, pt).empty()) return REMY_EINVAL;
+  if (!cands) n_cands = 1;
+  BatchPlan plan = plan_batch(cfgs, n_cfgs, n_cands);
+  if (link_cap_override) plan.link_cap = link_cap_override;
+  const uint32_t n_sims = n_cands * n_cfgs;
+  std::vector<SenderCold> cold(plan.n_max);
+  std::vector<DelayEnt> dring(plan.delay_cap);
+  std::vector<uint32_t> cnt(tree->n_leaves);
+  std::vector<double> hot(2 * plan.n_max);
+  if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * (size_t)n_cands * tree->n_leaves);
+  uint32_t cap = plan.link_cap;
+  std::vector<uint32_t> todo = plan.order;
+  for (int round = 0; round < 5 && !todo.empty(); round++) {
+    std::vector<LinkEnt> lring(cap);
+    KernelArgs A;
+    memset(&A, 0, sizeof A);
+    A.bounds = pt.bounds.data(); A.meta = pt.meta.data(); A.leaves = pt.leaves.data();
+    A.n_nodes = tree->n_nodes; A.n_leaves = tree->n_leaves; A.axes_mask = pt.axes_mask; A.tree_in_smem = 0;
+    A.cands = cands; A.cfgs = cfgs; A.seeds = seeds; A.n_cfgs = n_cfgs;
+    A.n_max = plan.n_max; A.link_cap = cap; A.delay_cap = plan.delay_cap;
+    A.out_sims = out_sims; A.out_senders = out_senders; A.sender_stride = sender_stride; A.out_use_counts = out_use_counts;
+    TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.axes_mask = A.axes_mask;
+    std::vector<uint32_t> redo;
+    for (uint32_t sim : todo) {
+      if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + plan.n_max, cold.data(), lring.data(), dring.data(), cnt.data());
+      else run_sim<false>(A, T, sim, hot.data(), hot.data() + plan.n_max, cold.data(), lring.data(), dring.data(), nullptr);
+      if (out_sims[sim].error & REMY_ERR_LINK_OVERFLOW) redo.push_back(sim);
+    }
+    todo.swap(redo);
+    if (cap >= (1u << 24)) break;
+    cap *= 16;
+  }
+  return 0;
+}
