@@ -81,7 +81,7 @@ struct BatchPlan {
   std::vector<uint32_t> order; /* simulation ids, most expensive first, grouped by num_senders */
 };
 
-constexpr uint32_t LINK_CAP_FIRST_TRY = 4096; /* for limits above this (incl. "infinite"); grown on overflow */
+constexpr uint32_t LINK_CAP_FIRST_TRY = 16384; /* for limits above this (incl. "infinite"); grown on overflow */
 
 inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t n_cands)
 {

@@ -23,6 +23,13 @@
 
 using namespace remy;
 
+/* Builds the list of simulations whose link queue outgrew the ring they were given. */
+__global__ void remy_collect_overflow(const RemySimResult *sims, uint32_t n_sims, uint32_t *list, uint32_t *count)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_sims && (sims[i].error & REMY_ERR_LINK_OVERFLOW)) list[atomicAdd(count, 1u)] = i;
+}
+
 namespace {
 
 thread_local std::string g_err;
@@ -63,7 +70,7 @@ struct RemyBatch {
   /* device */
   DevBuf<Bounds> bounds; DevBuf<DevNodeMeta> meta; DevBuf<DevLeaf> leaves;
   DevBuf<RemyLeafOverride> d_cands; DevBuf<RemyNetConfig> d_cfgs; DevBuf<uint32_t> d_seeds;
-  DevBuf<uint32_t> order; DevBuf<uint32_t> work_counter;
+  DevBuf<uint32_t> order; DevBuf<uint32_t> work_counter; DevBuf<uint32_t> redo_list; DevBuf<uint32_t> redo_count;
   DevBuf<RemySimResult> out_sims; DevBuf<RemySenderResult> out_senders; DevBuf<uint32_t> out_counts;
   Scratch scratch;
   uint32_t grid = 0; size_t smem = 0;
@@ -196,7 +203,7 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   const uint32_t link_cap = plan.link_cap, delay_cap = plan.delay_cap;
   const std::vector<uint32_t> &order = plan.order;
 
-  CU(b->d_cfgs.alloc(n_cfgs)); CU(b->d_seeds.alloc(n_cfgs)); CU(b->order.alloc(b->n_sims)); CU(b->work_counter.alloc(1));
+  CU(b->d_cfgs.alloc(n_cfgs)); CU(b->d_seeds.alloc(n_cfgs)); CU(b->order.alloc(b->n_sims)); CU(b->work_counter.alloc(1)); CU(b->redo_list.alloc(b->n_sims)); CU(b->redo_count.alloc(1));
   CU(cudaMemcpyAsync(b->d_cfgs.p, cfgs, n_cfgs * sizeof(RemyNetConfig), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(b->d_seeds.p, seeds, n_cfgs * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(b->order.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
@@ -234,7 +241,35 @@ int remy_b200_batch_run(RemyBatch *b, float *kernel_ms)
   b->launches = 0;
   if (b->want_counts) CU(cudaMemsetAsync(b->out_counts.p, 0, b->out_counts.n * sizeof(uint32_t), g_stream));
   if (kernel_ms) CU(cudaEventRecord(b->ev0, g_stream));
-  if (b->n_sims) { int rc = launch(b, b->scratch, b->order.p, b->n_sims, b->grid); if (rc) return rc; }
+  if (b->n_sims) {
+    int rc = launch(b, b->scratch, b->order.p, b->n_sims, b->grid);
+    if (rc) return rc;
+    /* Simulations whose link queue outgrew the ring are re-run with larger rings, inside
+     * the timed region.  (The reference's deque is unbounded; a finite ring is this
+     * library's artefact, so it is hidden from the caller as long as memory allows.) */
+    uint32_t cap = b->scratch.link_cap;
+    for (int round = 0; round < 3 && cap < (1u << 24); round++) {
+      CU(cudaMemsetAsync(b->redo_count.p, 0, sizeof(uint32_t), g_stream));
+      remy_collect_overflow<<<(b->n_sims + 255) / 256, 256, 0, g_stream>>>(b->out_sims.p, b->n_sims, b->redo_list.p, b->redo_count.p);
+      CU(cudaGetLastError());
+      b->launches++;
+      uint32_t n_redo = 0;
+      CU(cudaMemcpyAsync(&n_redo, b->redo_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream));
+      CU(cudaStreamSynchronize(g_stream));
+      if (n_redo == 0) break;
+      cap = (uint32_t)std::min<uint64_t>((uint64_t)cap * 16, 1u << 24);
+      const size_t per_slot = (size_t)cap * sizeof(LinkEnt);
+      const size_t budget = (size_t)32 << 30;
+      uint32_t slots = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_slot, SIM_BLOCK), n_redo);
+      slots = ((slots + SIM_BLOCK - 1) / SIM_BLOCK) * SIM_BLOCK;
+      Scratch s2;
+      rc = alloc_scratch(b, s2, slots, cap, b->scratch.delay_cap);
+      if (rc) return rc;
+      rc = launch(b, s2, b->redo_list.p, n_redo, slots / SIM_BLOCK);
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(g_stream)); /* s2 is freed at the end of this scope */
+    }
+  }
   if (kernel_ms) {
     CU(cudaEventRecord(b->ev1, g_stream));
     CU(cudaEventSynchronize(b->ev1));
@@ -254,33 +289,6 @@ int remy_b200_batch_fetch(RemyBatch *b, RemySimResult *out_sims, RemySenderResul
   CU(cudaSetDevice(g_device));
   CU(cudaMemcpyAsync(out_sims, b->out_sims.p, (size_t)b->n_sims * sizeof(RemySimResult), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
-
-  /* Simulations whose link queue outgrew the ring: re-run them with larger rings.
-   * (The reference's deque is unbounded; a finite ring is this library's artefact,
-   * so it is hidden from the caller as long as memory allows.) */
-  uint32_t cap = b->scratch.link_cap;
-  for (int round = 0; round < 4; round++) {
-    std::vector<uint32_t> redo;
-    for (uint32_t i = 0; i < b->n_sims; i++) if (out_sims[i].error & REMY_ERR_LINK_OVERFLOW) redo.push_back(i);
-    if (redo.empty()) break;
-    if (cap >= (1u << 24)) break;
-    cap = std::min<uint64_t>((uint64_t)cap * 16, 1u << 24);
-    const size_t per_slot = (size_t)cap * sizeof(LinkEnt);
-    const size_t budget = (size_t)24 << 30;
-    uint32_t slots = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_slot, SIM_BLOCK), redo.size());
-    slots = ((slots + SIM_BLOCK - 1) / SIM_BLOCK) * SIM_BLOCK;
-    Scratch s2;
-    int rc = alloc_scratch(b, s2, slots, cap, b->scratch.delay_cap);
-    if (rc) return rc;
-    DevBuf<uint32_t> d_redo;
-    CU(d_redo.alloc(redo.size()));
-    CU(cudaMemcpyAsync(d_redo.p, redo.data(), redo.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
-    rc = launch(b, s2, d_redo.p, (uint32_t)redo.size(), slots / SIM_BLOCK);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(g_stream));
-    for (uint32_t i : redo)
-      CU(cudaMemcpy(&out_sims[i], b->out_sims.p + i, sizeof(RemySimResult), cudaMemcpyDeviceToHost));
-  }
   if (out_senders)
     CU(cudaMemcpy(out_senders, b->out_senders.p, (size_t)b->n_sims * b->sender_stride * sizeof(RemySenderResult), cudaMemcpyDeviceToHost));
   if (out_use_counts)

@@ -71,3 +71,13 @@ def candidate_grid(leaf_index, base=(1, 1.0, 3.0), n=343):
     for k in range(len(arr)):
         arr[k] = cands[k]
     return arr
+
+
+def load_golden_tree(name):
+    """Flattened copies of the reference's tests/RemyCC-*.dna fixtures (tests/golden/trees,
+    made by tools/make_golden.py); "default" is WhiskerTree()."""
+    import os
+    if name == "default":
+        return abi.default_tree()
+    z = np.load(os.path.join(abi.REPO_ROOT, "tests", "golden", "trees", name + ".npz"))
+    return abi.FlatTree(z["nodes"], z["leaves"])

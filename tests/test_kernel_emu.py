@@ -1,0 +1,96 @@
+"""The CUDA kernel's event loop is a restructuring, not a translation, of the reference's
+loop.  These CPU tests compile the SAME kernel source (remy_b200/csrc/sim_kernel.cuh) with
+g++ through tests/emu/host_emu.h and check it against the oracle, so that logic errors are
+caught where there is no GPU.  (The GPU parity tests proper are in test_gpu_parity.py.)"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, assert_same_results, case_inputs, check_against_golden, load_vectors, random_candidates, random_configs
+from remy_b200 import abi, workloads
+
+
+class Emu(abi._ScoreLib):
+    def __init__(self):
+        super().__init__(os.path.join(ROOT, "tests", "emu", "libremy_emu.so"), "remy_emu_score_batch", (C.c_uint32,))
+
+    def score(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, link_cap=0):
+        return super().score(tree, cfgs, seeds, cands, want_senders, want_use_counts, extra=(link_cap,))
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    return Emu()
+
+
+@pytest.mark.parametrize("case", load_vectors(), ids=lambda c: c["name"])
+def test_emu_reproduces_golden(emu, case):
+    tree, cfgs, seeds, cands = case_inputs(case)
+    sims, snd, cnt = emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    check_against_golden(case, sims, snd, cnt, exact_utility=True)
+
+
+@pytest.mark.parametrize("tree_name", ["default", "RemyCC-2014-100x", "RemyCC-2013-delta0.1"])
+def test_emu_equals_oracle_random(emu, oracle, tree_name):
+    rng = np.random.default_rng(len(tree_name))
+    tree = workloads.load_golden_tree(tree_name)
+    cfgs = random_configs(rng, 30, max_ticks=1e4)
+    seeds = rng.integers(0, 2 ** 32, size=len(cfgs), dtype=np.uint64).astype(np.uint32)
+    cands = random_candidates(rng, tree, 3)
+    a = emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    b = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=4)
+    assert_same_results(a, b, exact_utility=True, what=tree_name)
+
+
+def test_emu_simultaneous_sends_and_ring_regrowth(emu, oracle):
+    """intersend 0 makes several senders transmit in the same tick (the only case in which
+    the shuffled order is observable); a 2-entry ring forces the overflow re-run path."""
+    tree = abi.default_tree()
+    rows = [dict(link_ppt=1, delay=d, num_senders=n, buffer_size=b, mean_on_duration=50, mean_off_duration=o,
+                 simulation_ticks=1500)
+            for d in (0, 1, 50) for n in (2, 3, 8, 31, 32) for b in (0, 5, abi.BUFFER_INFINITE) for o in (0, 20)]
+    cfgs = abi.make_configs(rows)
+    seeds = np.arange(len(rows), dtype=np.uint32) + 7
+    cands = np.zeros(3, dtype=abi.leaf_override_dtype)
+    cands[0] = (0.9, 0.0, 5, 0)     # bursts: windows up to 50 packets, no pacing
+    cands[1] = (0.5, 0.0, 0, 0)     # windows collapse to 0: Rat::send's repeated lookups
+    cands[2] = (1.0, 1.0, 1, 0)
+    want = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=4)
+    assert_same_results(emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True), want, what="burst")
+    assert int(want[0]["link_queued"].max()) > 64
+    assert_same_results(emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, link_cap=2), want, what="regrow")
+
+
+def test_emu_error_words(emu, oracle):
+    """exit(1)/assert paths of the reference become per-simulation error words."""
+    nodes = np.zeros(3, dtype=abi.tree_node_dtype)
+    leaves = np.zeros(2, dtype=abi.leaf_action_dtype)
+    nodes["upper"][:] = 163840.0
+    nodes["axis_mask"] = 15
+    nodes[0]["child_begin"], nodes[0]["child_count"] = 1, 2
+    nodes[1]["upper"][2] = 1.5
+    nodes[2]["lower"][2] = 2.0      # hole: rtt_ratio in [1.5, 2) matches no child
+    nodes[2]["leaf_index"] = 1
+    leaves[0] = (1.0, 0.5, 2, 0)
+    leaves[1] = (0.8, 1.0, 0, 0)
+    hole = abi.FlatTree(nodes, leaves)
+    cfgs = abi.make_configs([dict(link_ppt=1, delay=50, num_senders=n, simulation_ticks=20000) for n in (1, 4, 16)])
+    seeds = np.array([1, 2, 3], dtype=np.uint32)
+    a, b = emu.score(hole, cfgs, seeds), oracle.score(hole, cfgs, seeds)
+    assert (a[0]["error"] == abi.ERR_NO_CHILD).all() and (b[0]["error"] == abi.ERR_NO_CHILD).all()
+    assert (a[0]["event_ticks"] == b[0]["event_ticks"]).all()
+    root = nodes[:1].copy()
+    root[0]["child_count"] = 0
+    root[0]["upper"][2] = 1.2       # root does not cover rtt_ratio >= 1.2: "No whisker found"
+    small = abi.FlatTree(root, leaves[:1])
+    a, b = emu.score(small, cfgs, seeds), oracle.score(small, cfgs, seeds)
+    assert (a[0]["error"] == abi.ERR_NO_WHISKER).all() and (b[0]["error"] == abi.ERR_NO_WHISKER).all()
+    assert (a[0]["event_ticks"] == b[0]["event_ticks"]).all()
+    bad = abi.make_configs([dict(link_ppt=1, num_senders=0, simulation_ticks=100),
+                            dict(link_ppt=1, num_senders=2, simulation_ticks=0),
+                            dict(link_ppt=0, num_senders=2, simulation_ticks=10),
+                            dict(link_ppt=1, num_senders=33, simulation_ticks=10)])
+    a = emu.score(abi.default_tree(), bad, np.arange(4, dtype=np.uint32))
+    assert (a[0]["error"] == abi.ERR_BAD_CONFIG).all()

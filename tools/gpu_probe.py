@@ -6,13 +6,16 @@ import numpy as np
 from remy_b200 import abi, workloads
 
 ticks = float(sys.argv[1]) if len(sys.argv) > 1 else 1e4
-ncand = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-dev = abi.Device(0)
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+treename = sys.argv[3] if len(sys.argv) > 3 else "default"
+nmax = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+dev = abi.Device(0, path=os.environ.get("REMY_LIB"))
 tree = abi.default_tree()
-cfgs = workloads.default_config_range(ticks=ticks)
+if treename != "default":
+    tree = workloads.load_golden_tree(treename)
+cfgs = np.tile(workloads.default_config_range(ticks=ticks, nsrc=(1, nmax, 1)), reps)
 seeds = workloads.seeds_for(1, len(cfgs))
-cands = workloads.candidate_grid(0, n=ncand)
-b = dev.create_batch(tree, cfgs, seeds, cands=cands)
+b = dev.create_batch(tree, cfgs, seeds)
 for it in range(3):
     t0 = time.time(); ms = b.run(timed=True); t1 = time.time()
     sims, _, _ = b.fetch()
