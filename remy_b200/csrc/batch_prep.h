@@ -27,9 +27,73 @@ struct PreparedTree {
   std::vector<Bounds> bounds;     /* [n_nodes][NAX] */
   std::vector<DevNodeMeta> meta;  /* [n_nodes] */
   std::vector<DevLeaf> leaves;    /* [n_leaves] */
+  std::vector<double> cuts;       /* per interior node with a table: its cuts, axis after axis */
+  std::vector<uint16_t> table;    /* per interior node with a table: first matching child per cell */
   uint32_t axes_mask = 0;
-  size_t bytes() const { return bounds.size() * sizeof(Bounds) + meta.size() * sizeof(DevNodeMeta) + leaves.size() * sizeof(DevLeaf); }
+  size_t bytes() const
+  {
+    return bounds.size() * sizeof(Bounds) + meta.size() * sizeof(DevNodeMeta) + leaves.size() * sizeof(DevLeaf)
+           + cuts.size() * sizeof(double) + ((table.size() * sizeof(uint16_t) + 15) / 16) * 16;
+  }
 };
+
+constexpr size_t MAX_TABLE_CELLS = 4096;   /* per node; larger nodes keep the linear scan */
+constexpr size_t MAX_TABLE_TOTAL = 32768;  /* whole tree (64 KB of uint16) */
+
+/* Evaluate the reference's first-match child scan once per cell of the grid induced by the
+ * children's bounds (see DevNodeMeta).  For cell index p on an axis with sorted cuts c_0 < ... :
+ *   m >= lo  <=>  p > rank(lo)      m < hi  <=>  p <= rank(hi)
+ * where rank(v) is v's index among the cuts (-1 for -inf, ncuts for +inf). */
+inline void build_cell_table(PreparedTree &t, uint32_t node)
+{
+  DevNodeMeta &md = t.meta[node];
+  std::vector<double> cuts[NAX];
+  size_t cells = 1;
+  for (int a = 0; a < NAX; a++) {
+    if (!(t.axes_mask & (1u << a))) continue;
+    for (uint32_t c = 0; c < md.count; c++) {
+      const Bounds &b = t.bounds[(size_t)(md.first + c) * NAX + a];
+      if (b.lo != b.lo || b.hi != b.hi) return;           /* NaN bound: keep the linear scan */
+      if (std::isfinite(b.lo)) cuts[a].push_back(b.lo);
+      if (std::isfinite(b.hi)) cuts[a].push_back(b.hi);
+    }
+    std::sort(cuts[a].begin(), cuts[a].end());
+    cuts[a].erase(std::unique(cuts[a].begin(), cuts[a].end()), cuts[a].end());
+    if (cuts[a].size() > 255) return;
+    cells *= cuts[a].size() + 1;
+    if (cells > MAX_TABLE_CELLS) return;
+  }
+  if (md.count >= NO_CELL_CHILD || t.table.size() + cells > MAX_TABLE_TOTAL) return;
+  auto rank = [&](int a, double v) -> int {
+    if (v == -INFINITY) return -1;
+    if (v == INFINITY) return (int)cuts[a].size();
+    return (int)(std::lower_bound(cuts[a].begin(), cuts[a].end(), v) - cuts[a].begin());
+  };
+  md.table_off = (uint32_t)t.table.size();
+  md.cuts_off = (uint32_t)t.cuts.size();
+  for (int a = 0; a < NAX; a++) {
+    md.ncuts[a] = (uint8_t)cuts[a].size();
+    t.cuts.insert(t.cuts.end(), cuts[a].begin(), cuts[a].end());
+  }
+  t.table.resize(t.table.size() + cells, NO_CELL_CHILD);
+  std::vector<int> p(NAX, 0);
+  for (size_t cell = 0; cell < cells; cell++) {
+    size_t rem = cell;
+    for (int a = 0; a < NAX; a++) {
+      const size_t dim = (t.axes_mask & (1u << a)) ? cuts[a].size() + 1 : 1;
+      p[a] = (int)(rem % dim); rem /= dim;
+    }
+    for (uint32_t c = 0; c < md.count; c++) {
+      bool ok = true;
+      for (int a = 0; a < NAX && ok; a++) {
+        if (!(t.axes_mask & (1u << a))) continue;
+        const Bounds &b = t.bounds[(size_t)(md.first + c) * NAX + a];
+        ok = (p[a] > rank(a, b.lo)) && (p[a] <= rank(a, b.hi));
+      }
+      if (ok) { t.table[md.table_off + cell] = (uint16_t)c; break; }
+    }
+  }
+}
 
 /* Returns "" or a description of what is wrong with the tree. */
 inline std::string prepare_tree(const RemyFlatTree *tree, PreparedTree &out)
@@ -64,7 +128,11 @@ inline std::string prepare_tree(const RemyFlatTree *tree, PreparedTree &out)
     }
     out.meta[i].first = nd.child_count ? nd.child_begin : nd.leaf_index;
     out.meta[i].count = nd.child_count;
+    out.meta[i].table_off = NO_TABLE; out.meta[i].cuts_off = 0;
+    for (int a = 0; a < 8; a++) out.meta[i].ncuts[a] = 0;
   }
+  for (uint32_t i = 0; i < tree->n_nodes; i++)
+    if (tree->nodes[i].child_count) build_cell_table(out, i);
   for (uint32_t i = 0; i < tree->n_leaves; i++) {
     out.leaves[i].window_multiple = tree->leaves[i].window_multiple;
     out.leaves[i].intersend = tree->leaves[i].intersend;

@@ -68,7 +68,7 @@ struct RemyBatch {
   uint32_t sender_stride = 0; bool want_senders = false, want_counts = false, has_cands = false;
   uint32_t axes_mask = 0; bool tree_in_smem = false; size_t tree_bytes = 0;
   /* device */
-  DevBuf<Bounds> bounds; DevBuf<DevNodeMeta> meta; DevBuf<DevLeaf> leaves;
+  DevBuf<Bounds> bounds; DevBuf<DevNodeMeta> meta; DevBuf<DevLeaf> leaves; DevBuf<double> cuts; DevBuf<uint16_t> table;
   DevBuf<RemyLeafOverride> d_cands; DevBuf<RemyNetConfig> d_cfgs; DevBuf<uint32_t> d_seeds;
   DevBuf<uint32_t> order; DevBuf<uint32_t> work_counter; DevBuf<uint32_t> redo_list; DevBuf<uint32_t> redo_count;
   DevBuf<RemySimResult> out_sims; DevBuf<RemySenderResult> out_senders; DevBuf<uint32_t> out_counts;
@@ -90,6 +90,7 @@ KernelArgs make_args(RemyBatch *b, const Scratch &s, const uint32_t *order, uint
 {
   KernelArgs a;
   a.bounds = b->bounds.p; a.meta = b->meta.p; a.leaves = b->leaves.p;
+  a.cuts = b->cuts.p; a.table = b->table.p; a.n_cuts = (uint32_t)b->cuts.n; a.n_table = (uint32_t)b->table.n;
   a.n_nodes = b->n_nodes; a.n_leaves = b->n_leaves; a.axes_mask = b->axes_mask; a.tree_in_smem = b->tree_in_smem;
   a.cands = b->has_cands ? b->d_cands.p : nullptr; a.cfgs = b->d_cfgs.p; a.seeds = b->d_seeds.p;
   a.order = order; a.n_cfgs = b->n_cfgs; a.n_work = n_work; a.work_counter = b->work_counter.p;
@@ -195,6 +196,9 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   CU(cudaMemcpyAsync(b->bounds.p, pt.bounds.data(), pt.bounds.size() * sizeof(Bounds), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(b->meta.p, pt.meta.data(), pt.meta.size() * sizeof(DevNodeMeta), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(b->leaves.p, pt.leaves.data(), pt.leaves.size() * sizeof(DevLeaf), cudaMemcpyHostToDevice, g_stream));
+  CU(b->cuts.alloc(pt.cuts.size())); CU(b->table.alloc(pt.table.size()));
+  if (!pt.cuts.empty()) CU(cudaMemcpyAsync(b->cuts.p, pt.cuts.data(), pt.cuts.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  if (!pt.table.empty()) CU(cudaMemcpyAsync(b->table.p, pt.table.data(), pt.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, g_stream));
 
   /* ---- configs: n_max, ring sizes, cost-sorted order ---- */
   const BatchPlan plan = plan_batch(cfgs, n_cfgs, n_cands);

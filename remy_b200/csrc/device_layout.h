@@ -48,7 +48,21 @@ static_assert(sizeof(LinkEnt) == 16 && sizeof(DelayEnt) == 32, "ring entry sizes
 /* Device copy of the tree: bounds[node][axis] = (lower, upper) with axes a node does not
  * test widened to (-inf, +inf); meta[node] = (child_begin or leaf_index, child_count). */
 struct REMY_ALIGN(16) Bounds { double lo, hi; };
-struct DevNodeMeta { uint32_t first; uint32_t count; };
+/* An interior node may carry a *cell table*: the distinct finite bounds of its children on
+ * each axis ("cuts") split the axis into ncuts+1 cells; a query's cell index p_a = #{cuts <= m[a]}
+ * decides every children's `lower <= m < upper` test at once, so table[cell] holds the first
+ * child (in stored order) whose box contains that cell, or NO_CELL_CHILD.  This is exactly the
+ * reference's first-match scan (src/whiskertree.cc:62-82) evaluated per cell on the host. */
+constexpr uint32_t NO_TABLE = 0xFFFFFFFFu;
+constexpr uint16_t NO_CELL_CHILD = 0xFFFFu;
+struct DevNodeMeta {
+  uint32_t first;       /* child_begin, or leaf_index when count == 0 */
+  uint32_t count;       /* number of children */
+  uint32_t table_off;   /* offset into the cell-table array, or NO_TABLE (linear scan) */
+  uint32_t cuts_off;    /* offset into the cuts array; axes concatenated in axis order */
+  uint8_t ncuts[8];     /* cuts per axis (0 for axes the tree never tests) */
+};
+static_assert(sizeof(DevNodeMeta) == 24, "DevNodeMeta layout");
 struct REMY_ALIGN(8) DevLeaf { double window_multiple; double intersend; int32_t window_increment; uint32_t pad; };
 
 } // namespace remy

@@ -62,6 +62,7 @@ struct KernelArgs {
   const Bounds *bounds;        /* [n_nodes][NAX] */
   const DevNodeMeta *meta;     /* [n_nodes] */
   const DevLeaf *leaves;       /* [n_leaves] */
+  const double *cuts; const uint16_t *table; uint32_t n_cuts, n_table; /* cell tables (device_layout.h) */
   uint32_t n_nodes, n_leaves, axes_mask, tree_in_smem;
   /* batch */
   const RemyLeafOverride *cands; /* [n_cands] or nullptr */
@@ -171,6 +172,7 @@ __device__ REMY_NOINLINE void shuffle_materialise(uint32_t x, uint32_t n, uint8_
 /* ------------------------------------------------------------- whiskers --- */
 struct TreeView {
   const Bounds *bounds;  const DevNodeMeta *meta; const DevLeaf *leaves;
+  const double *cuts; const uint16_t *table;
   uint32_t axes_mask;
 };
 
@@ -197,8 +199,25 @@ __device__ __forceinline__ uint32_t find_leaf(const TreeView &T, const double *m
     const DevNodeMeta md = T.meta[cur];
     if (md.count == 0) return md.first;
     uint32_t next = 0xFFFFFFFFu;
-    for (uint32_t c = 0; c < md.count; c++) {
-      if (node_contains(T, md.first + c, m)) { next = md.first + c; break; }
+    if (md.table_off != NO_TABLE) {
+      /* cell lookup: p_a = #{cuts <= m[a]} per axis, then one table read */
+      const double *cp = T.cuts + md.cuts_off;
+      uint32_t idx = 0, stride = 1;
+#pragma unroll
+      for (int a = 0; a < NAX; a++) {
+        if (T.axes_mask & (1u << a)) {
+          const uint32_t nc = md.ncuts[a];
+          uint32_t p = 0;
+          for (uint32_t k = 0; k < nc; k++) p += (m[a] >= cp[k]) ? 1u : 0u;
+          idx += p * stride; stride *= nc + 1; cp += nc;
+        }
+      }
+      const uint32_t c = T.table[md.table_off + idx];
+      if (c != NO_CELL_CHILD) next = md.first + c;
+    } else {
+      for (uint32_t c = 0; c < md.count; c++) {
+        if (node_contains(T, md.first + c, m)) { next = md.first + c; break; }
+      }
     }
     if (next == 0xFFFFFFFFu) { err |= REMY_ERR_NO_CHILD; return 0xFFFFFFFFu; }
     cur = next;
@@ -574,13 +593,17 @@ __global__ void __launch_bounds__(SIM_BLOCK) remy_sim_kernel(const KernelArgs A)
     Bounds *sb = reinterpret_cast<Bounds *>(p);
     DevLeaf *sl = reinterpret_cast<DevLeaf *>(sb + (size_t)A.n_nodes * NAX);
     DevNodeMeta *sm = reinterpret_cast<DevNodeMeta *>(sl + A.n_leaves);
+    double *sc = reinterpret_cast<double *>(sm + A.n_nodes);
+    uint16_t *st = reinterpret_cast<uint16_t *>(sc + A.n_cuts);
+    for (uint32_t i = threadIdx.x; i < A.n_cuts; i += blockDim.x) sc[i] = A.cuts[i];
+    for (uint32_t i = threadIdx.x; i < A.n_table; i += blockDim.x) st[i] = A.table[i];
     for (uint32_t i = threadIdx.x; i < A.n_nodes * NAX; i += blockDim.x) sb[i] = A.bounds[i];
     for (uint32_t i = threadIdx.x; i < A.n_leaves; i += blockDim.x) sl[i] = A.leaves[i];
     for (uint32_t i = threadIdx.x; i < A.n_nodes; i += blockDim.x) sm[i] = A.meta[i];
     __syncthreads();
-    T.bounds = sb; T.leaves = sl; T.meta = sm;
+    T.bounds = sb; T.leaves = sl; T.meta = sm; T.cuts = sc; T.table = st;
   } else {
-    T.bounds = A.bounds; T.leaves = A.leaves; T.meta = A.meta;
+    T.bounds = A.bounds; T.leaves = A.leaves; T.meta = A.meta; T.cuts = A.cuts; T.table = A.table;
   }
   const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   SenderCold *cold = A.cold + slot * A.n_max;

@@ -38,11 +38,12 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
     KernelArgs A;
     memset(&A, 0, sizeof A);
     A.bounds = pt.bounds.data(); A.meta = pt.meta.data(); A.leaves = pt.leaves.data();
+    A.cuts = pt.cuts.data(); A.table = pt.table.data(); A.n_cuts = (uint32_t)pt.cuts.size(); A.n_table = (uint32_t)pt.table.size();
     A.n_nodes = tree->n_nodes; A.n_leaves = tree->n_leaves; A.axes_mask = pt.axes_mask; A.tree_in_smem = 0;
     A.cands = cands; A.cfgs = cfgs; A.seeds = seeds; A.n_cfgs = n_cfgs;
     A.n_max = plan.n_max; A.link_cap = cap; A.delay_cap = plan.delay_cap;
     A.out_sims = out_sims; A.out_senders = out_senders; A.sender_stride = sender_stride; A.out_use_counts = out_use_counts;
-    TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.axes_mask = A.axes_mask;
+    TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
     std::vector<uint32_t> redo;
     for (uint32_t sim : todo) {
       if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + plan.n_max, cold.data(), lring.data(), dring.data(), cnt.data());

@@ -66,6 +66,31 @@ def test_gpu_link_ring_overflow_is_rerun(device, oracle):
     assert_same_results(got, want, exact_utility=False, what="overflow")
 
 
+@pytest.mark.parametrize("kind", ["irregular", "grid", "wide", "six-axes"])
+def test_gpu_irregular_trees(device, oracle, kind):
+    """Cell-table lookups (batch_prep.h::build_cell_table) and the linear fallback against the
+    oracle's first-match scan on trees with overlapping children, holes and six axes."""
+    from helpers import random_tree
+    rng = np.random.default_rng({"irregular": 11, "grid": 12, "wide": 13, "six-axes": 14}[kind])
+    for rep in range(4):
+        if kind == "grid":
+            tree = random_tree(rng, depth=2, grid=True)
+        elif kind == "wide":
+            tree = random_tree(rng, n_children=40, depth=1)
+        elif kind == "six-axes":
+            tree = random_tree(rng, n_children=5, depth=2, axes_mask=0b111111)
+        else:
+            tree = random_tree(rng, n_children=6, depth=2)
+        cfgs = abi.make_configs([dict(link_ppt=float(l), delay=float(d), num_senders=int(n), buffer_size=int(b),
+                                      mean_on_duration=500.0, mean_off_duration=200.0, simulation_ticks=4000.0)
+                                 for l, d, n, b in zip(rng.choice([0.5, 1, 2, 5], 32), rng.choice([10, 50, 150], 32),
+                                                       rng.integers(1, 33, 32), rng.choice([5, 50, abi.BUFFER_INFINITE], 32))])
+        seeds = rng.integers(0, 2 ** 32, size=len(cfgs), dtype=np.uint64).astype(np.uint32)
+        got = device.score(tree, cfgs, seeds, want_use_counts=True)
+        want = oracle.score(tree, cfgs, seeds, want_use_counts=True, threads=16)
+        assert_same_results(got, want, exact_utility=False, what=f"{kind}/{rep}")
+
+
 def test_gpu_error_words(device):
     nodes = np.zeros(3, dtype=abi.tree_node_dtype)
     leaves = np.zeros(2, dtype=abi.leaf_action_dtype)

@@ -94,3 +94,30 @@ def test_emu_error_words(emu, oracle):
                             dict(link_ppt=1, num_senders=33, simulation_ticks=10)])
     a = emu.score(abi.default_tree(), bad, np.arange(4, dtype=np.uint32))
     assert (a[0]["error"] == abi.ERR_BAD_CONFIG).all()
+
+
+@pytest.mark.parametrize("kind", ["irregular", "grid", "wide", "six-axes"])
+def test_emu_irregular_trees(emu, oracle, kind):
+    """The kernel answers lookups from per-node cell tables built on the host
+    (batch_prep.h::build_cell_table) and falls back to the linear first-match scan for nodes
+    whose table would be too large.  Overlapping children, holes and all six axes must give
+    the oracle's leaf (or the oracle's error word) every time."""
+    from helpers import random_tree
+    rng = np.random.default_rng({"irregular": 1, "grid": 2, "wide": 3, "six-axes": 4}[kind])
+    for rep in range(4):
+        if kind == "grid":
+            tree = random_tree(rng, depth=2, grid=True)
+        elif kind == "wide":
+            tree = random_tree(rng, n_children=40, depth=1)   # > 4096 cells: linear fallback
+        elif kind == "six-axes":
+            tree = random_tree(rng, n_children=5, depth=2, axes_mask=0b111111)
+        else:
+            tree = random_tree(rng, n_children=6, depth=2)
+        cfgs = abi.make_configs([dict(link_ppt=float(l), delay=float(d), num_senders=int(n), buffer_size=int(b),
+                                      mean_on_duration=500.0, mean_off_duration=200.0, simulation_ticks=4000.0)
+                                 for l, d, n, b in zip(rng.choice([0.5, 1, 2, 5], 12), rng.choice([10, 50, 150], 12),
+                                                       rng.integers(1, 17, 12), rng.choice([5, 50, abi.BUFFER_INFINITE], 12))])
+        seeds = rng.integers(0, 2 ** 32, size=len(cfgs), dtype=np.uint64).astype(np.uint32)
+        a = emu.score(tree, cfgs, seeds, want_use_counts=True)
+        b = oracle.score(tree, cfgs, seeds, want_use_counts=True, threads=4)
+        assert_same_results(a, b, what=f"{kind}/{rep}")
