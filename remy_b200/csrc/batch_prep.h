@@ -142,14 +142,32 @@ inline std::string prepare_tree(const RemyFlatTree *tree, PreparedTree &out)
   return "";
 }
 
+/* One kernel launch: simulations whose num_senders falls in the same bucket.  Shared
+ * memory per thread grows with the bucket's largest num_senders, so small-n buckets run
+ * with (many) more resident threads per SM than one launch sized for n = 32 would. */
+struct PassPlan {
+  uint32_t n_max;     /* largest num_senders the pass accepts */
+  uint32_t begin, end;/* range of BatchPlan::order */
+};
+
 struct BatchPlan {
-  uint32_t n_max = 1;       /* largest valid num_senders */
+  uint32_t n_max = 1;       /* largest valid num_senders in the batch */
   uint32_t link_cap = 1;    /* ring entries per slot (power of two) */
   uint32_t delay_cap = 8;
-  std::vector<uint32_t> order; /* simulation ids, most expensive first, grouped by num_senders */
+  std::vector<uint32_t> order; /* simulation ids: by bucket, then num_senders, then cost, descending */
+  std::vector<PassPlan> passes;
 };
 
 constexpr uint32_t LINK_CAP_FIRST_TRY = 16384; /* for limits above this (incl. "infinite"); grown on overflow */
+
+inline uint32_t sender_bucket(uint32_t n)
+{
+  if (n == 0 || n > REMY_MAX_SENDERS) return 4; /* rejected by the kernel; any pass will do */
+  if (n <= 4) return 4;
+  if (n <= 8) return 8;
+  if (n <= 16) return 16;
+  return 32;
+}
 
 inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t n_cands)
 {
@@ -170,15 +188,28 @@ inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t
   p.order.resize(n_sims);
   for (uint32_t i = 0; i < n_sims; i++) p.order[i] = i;
   std::vector<double> cost(n_cfgs);
-  for (uint32_t k = 0; k < n_cfgs; k++) cost[k] = cfgs[k].link_ppt * cfgs[k].simulation_ticks;
+  std::vector<uint32_t> bucket(n_cfgs);
+  for (uint32_t k = 0; k < n_cfgs; k++) {
+    cost[k] = cfgs[k].link_ppt * cfgs[k].simulation_ticks;
+    bucket[k] = sender_bucket(cfgs[k].num_senders);
+  }
   /* instances sorted by config: same num_senders together (same loop trip counts in a
-   * warp), longest first (the tail of the batch is made of the shortest simulations) */
+   * warp), longest first (the tail of each pass is made of its shortest simulations) */
   std::stable_sort(p.order.begin(), p.order.end(), [&](uint32_t x, uint32_t y) {
     const uint32_t kx = x % n_cfgs, ky = y % n_cfgs;
+    if (bucket[kx] != bucket[ky]) return bucket[kx] > bucket[ky];
     if (cfgs[kx].num_senders != cfgs[ky].num_senders) return cfgs[kx].num_senders > cfgs[ky].num_senders;
     if (cost[kx] != cost[ky]) return cost[kx] > cost[ky];
     return kx < ky;
   });
+  for (uint32_t i = 0; i < n_sims;) {
+    const uint32_t bk = bucket[p.order[i] % n_cfgs];
+    uint32_t j = i;
+    while (j < n_sims && bucket[p.order[j] % n_cfgs] == bk) j++;
+    PassPlan pp; pp.n_max = bk; pp.begin = i; pp.end = j;
+    p.passes.push_back(pp);
+    i = j;
+  }
   return p;
 }
 

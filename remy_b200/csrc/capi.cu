@@ -2,11 +2,11 @@
  * capi.cu — implementation of include/remy_b200.h on top of the sm_100a kernel.
  *
  * Host side of the boundary only: argument checking, flattening the tree into
- * the device layout, the cost-sorted work list (instances sorted by config so
- * that neighbouring threads run similar simulations), scratch sizing, kernel
- * launches on the library's stream, and the bounded re-run of simulations whose
- * link queue outgrew the ring they were given.  There is no CPU implementation
- * of the simulator in this library: without a CUDA device every entry point
+ * the device layout (with the per-node cell tables), the config-sorted work
+ * list split into passes by sender count, scratch sizing, kernel launches on
+ * the library's streams, and the bounded re-run of simulations whose link
+ * queue outgrew the ring they were given.  There is no CPU implementation of
+ * the simulator in this library: without a CUDA device every entry point
  * fails with REMY_ENODEV.
  */
 #include <algorithm>
@@ -36,7 +36,9 @@ thread_local std::string g_err;
 std::mutex g_mu;           /* the library is callable from several host threads; calls serialise */
 int g_device = -1;
 int g_sms = 0;
-cudaStream_t g_stream = nullptr;
+constexpr int MAX_PASSES = 4;
+cudaStream_t g_stream = nullptr;             /* main stream: copies, events, re-runs */
+cudaStream_t g_pass_stream[MAX_PASSES] = {}; /* one per concurrent pass */
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
@@ -54,69 +56,106 @@ template <class T> struct DevBuf {
   ~DevBuf() { free(); }
 };
 
+/* Per-slot working memory of one pass (slot = one resident thread). */
 struct Scratch {
-  DevBuf<SenderCold> cold; DevBuf<LinkEnt> link; DevBuf<DelayEnt> delay; DevBuf<uint32_t> counts;
-  uint32_t slots = 0, link_cap = 0, delay_cap = 0;
+  DevBuf<SenderCold> cold; DevBuf<double> share; DevBuf<LinkEnt> link; DevBuf<DelayEnt> delay; DevBuf<uint32_t> counts;
+  uint32_t slots = 0, n_max = 0, link_cap = 0, delay_cap = 0;
+  static size_t bytes_per_slot(uint32_t n_max, uint32_t link_cap, uint32_t delay_cap, uint32_t count_leaves)
+  {
+    return (size_t)n_max * (sizeof(SenderCold) + sizeof(double)) + (size_t)link_cap * sizeof(LinkEnt)
+           + (size_t)delay_cap * sizeof(DelayEnt) + (size_t)count_leaves * sizeof(uint32_t);
+  }
+};
+
+struct Pass {
+  uint32_t n_max = 0, begin = 0, n_work = 0, grid = 0;
+  size_t smem = 0; bool tree_in_smem = false;
+  Scratch scratch;
+  DevBuf<uint32_t> counter;
+  cudaEvent_t done = nullptr;
 };
 
 } // namespace
 
 struct RemyBatch {
-  /* host copies */
-  std::vector<RemyNetConfig> cfgs; std::vector<uint32_t> seeds; std::vector<RemyLeafOverride> cands;
-  uint32_t n_cands = 1, n_cfgs = 0, n_sims = 0, n_leaves = 0, n_nodes = 0, n_max = 1;
+  uint32_t n_cands = 1, n_cfgs = 0, n_sims = 0, n_leaves = 0, n_nodes = 0;
   uint32_t sender_stride = 0; bool want_senders = false, want_counts = false, has_cands = false;
-  uint32_t axes_mask = 0; bool tree_in_smem = false; size_t tree_bytes = 0;
+  uint32_t axes_mask = 0; size_t tree_bytes = 0;
+  uint32_t delay_cap = 8;
   /* device */
   DevBuf<Bounds> bounds; DevBuf<DevNodeMeta> meta; DevBuf<DevLeaf> leaves; DevBuf<double> cuts; DevBuf<uint16_t> table;
   DevBuf<RemyLeafOverride> d_cands; DevBuf<RemyNetConfig> d_cfgs; DevBuf<uint32_t> d_seeds;
-  DevBuf<uint32_t> order; DevBuf<uint32_t> work_counter; DevBuf<uint32_t> redo_list; DevBuf<uint32_t> redo_count;
+  DevBuf<uint32_t> order; DevBuf<uint32_t> redo_list; DevBuf<uint32_t> redo_count; DevBuf<uint32_t> redo_counter;
   DevBuf<RemySimResult> out_sims; DevBuf<RemySenderResult> out_senders; DevBuf<uint32_t> out_counts;
-  Scratch scratch;
-  uint32_t grid = 0; size_t smem = 0;
+  std::vector<std::unique_ptr<Pass>> passes;
   uint32_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ran = false;
+  ~RemyBatch()
+  {
+    for (auto &p : passes) if (p->done) cudaEventDestroy(p->done);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+  }
 };
 
 namespace {
 
-size_t smem_bytes(const RemyBatch *b, bool with_tree)
+size_t smem_bytes(const RemyBatch *b, uint32_t n_max, bool with_tree)
 {
-  return (size_t)2 * b->n_max * SIM_BLOCK * sizeof(double) + (with_tree ? b->tree_bytes : 0);
+  return (size_t)(INC_BUF + n_max) * SIM_BLOCK * sizeof(double) + (with_tree ? b->tree_bytes : 0);
 }
 
-KernelArgs make_args(RemyBatch *b, const Scratch &s, const uint32_t *order, uint32_t n_work)
+const void *kernel_fn(const RemyBatch *b)
+{
+  return b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
+}
+
+KernelArgs make_args(RemyBatch *b, const Scratch &s, bool tree_in_smem, const uint32_t *order, uint32_t n_work, uint32_t *counter)
 {
   KernelArgs a;
   a.bounds = b->bounds.p; a.meta = b->meta.p; a.leaves = b->leaves.p;
   a.cuts = b->cuts.p; a.table = b->table.p; a.n_cuts = (uint32_t)b->cuts.n; a.n_table = (uint32_t)b->table.n;
-  a.n_nodes = b->n_nodes; a.n_leaves = b->n_leaves; a.axes_mask = b->axes_mask; a.tree_in_smem = b->tree_in_smem;
+  a.n_nodes = b->n_nodes; a.n_leaves = b->n_leaves; a.axes_mask = b->axes_mask; a.tree_in_smem = tree_in_smem;
   a.cands = b->has_cands ? b->d_cands.p : nullptr; a.cfgs = b->d_cfgs.p; a.seeds = b->d_seeds.p;
-  a.order = order; a.n_cfgs = b->n_cfgs; a.n_work = n_work; a.work_counter = b->work_counter.p;
-  a.cold = s.cold.p; a.n_max = b->n_max; a.link_ring = s.link.p; a.link_cap = s.link_cap;
+  a.order = order; a.n_cfgs = b->n_cfgs; a.n_work = n_work; a.work_counter = counter;
+  a.cold = s.cold.p; a.share = s.share.p; a.n_max = s.n_max; a.link_ring = s.link.p; a.link_cap = s.link_cap;
   a.delay_ring = s.delay.p; a.delay_cap = s.delay_cap; a.slot_counts = s.counts.p;
   a.out_sims = b->out_sims.p; a.out_senders = b->want_senders ? b->out_senders.p : nullptr;
   a.sender_stride = b->sender_stride; a.out_use_counts = b->want_counts ? b->out_counts.p : nullptr;
   return a;
 }
 
-int alloc_scratch(RemyBatch *b, Scratch &s, uint32_t slots, uint32_t link_cap, uint32_t delay_cap)
+int alloc_scratch(RemyBatch *b, Scratch &s, uint32_t slots, uint32_t n_max, uint32_t link_cap, uint32_t delay_cap)
 {
-  s.slots = slots; s.link_cap = link_cap; s.delay_cap = delay_cap;
-  CU(s.cold.alloc((size_t)slots * b->n_max));
+  s.slots = slots; s.n_max = n_max; s.link_cap = link_cap; s.delay_cap = delay_cap;
+  CU(s.cold.alloc((size_t)slots * n_max));
+  CU(s.share.alloc((size_t)slots * n_max));
   CU(s.link.alloc((size_t)slots * link_cap));
   CU(s.delay.alloc((size_t)slots * delay_cap));
   if (b->want_counts) CU(s.counts.alloc((size_t)slots * b->n_leaves));
   return 0;
 }
 
-int launch(RemyBatch *b, const Scratch &s, const uint32_t *order, uint32_t n_work, uint32_t grid)
+/* Shared memory and residency of the kernel for a pass that accepts up to n_max senders. */
+int pass_geometry(RemyBatch *b, uint32_t n_max, size_t &smem, bool &tree_in_smem, uint32_t &resident_blocks)
 {
-  CU(cudaMemsetAsync(b->work_counter.p, 0, sizeof(uint32_t), g_stream));
-  const KernelArgs a = make_args(b, s, order, n_work);
-  if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, b->smem, g_stream>>>(a);
-  else remy_sim_kernel<false><<<grid, SIM_BLOCK, b->smem, g_stream>>>(a);
+  tree_in_smem = smem_bytes(b, n_max, true) <= 160 * 1024 && b->tree_bytes <= 64 * 1024;
+  smem = smem_bytes(b, n_max, tree_in_smem);
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_fn(b), SIM_BLOCK, smem));
+  if (per_sm < 1) return fail(REMY_ECUDA, "kernel does not fit on an SM");
+  resident_blocks = (uint32_t)per_sm * (uint32_t)g_sms;
+  return 0;
+}
+
+int launch(RemyBatch *b, const Scratch &s, size_t smem, bool tree_in_smem, const uint32_t *order, uint32_t n_work,
+           uint32_t grid, uint32_t *counter, cudaStream_t stream)
+{
+  CU(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
+  const KernelArgs a = make_args(b, s, tree_in_smem, order, n_work, counter);
+  if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else remy_sim_kernel<false><<<grid, SIM_BLOCK, smem, stream>>>(a);
   CU(cudaGetLastError());
   b->launches++;
   return 0;
@@ -145,6 +184,13 @@ int remy_b200_init(int device)
     return fail(REMY_ENODEV, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "); this library is built for sm_100a only");
   if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < MAX_PASSES; i++) {
+    if (g_pass_stream[i]) { cudaStreamDestroy(g_pass_stream[i]); g_pass_stream[i] = nullptr; }
+    CU(cudaStreamCreateWithFlags(&g_pass_stream[i], cudaStreamNonBlocking));
+  }
+  /* the kernel stages the tree in shared memory: allow the large carve-out */
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_device = device; g_sms = prop.multiProcessorCount;
   g_err.clear();
   return 0;
@@ -154,6 +200,8 @@ void remy_b200_shutdown(void)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  for (int i = 0; i < MAX_PASSES; i++)
+    if (g_pass_stream[i]) { cudaStreamDestroy(g_pass_stream[i]); g_pass_stream[i] = nullptr; }
   g_device = -1;
 }
 
@@ -169,19 +217,17 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   if (g_device < 0 || !g_stream) return fail(REMY_ENODEV, "remy_b200_init has not been called");
   if (!tree || !tree->nodes || !tree->leaves || tree->n_nodes == 0 || tree->n_leaves == 0)
     return fail(REMY_EINVAL, "empty tree");
-  if (!cfgs || !seeds) return fail(REMY_EINVAL, "cfgs/seeds is NULL");
+  if (n_cfgs && (!cfgs || !seeds)) return fail(REMY_EINVAL, "cfgs/seeds is NULL");
   if (!cands) n_cands = 1;
   if ((uint64_t)n_cands * n_cfgs > 0x7fffffffull) return fail(REMY_EINVAL, "too many simulations in one batch");
   CU(cudaSetDevice(g_device));
 
-  RemyBatch *b = new RemyBatch();
-  std::unique_ptr<RemyBatch> guard(b);
+  std::unique_ptr<RemyBatch> guard(new RemyBatch());
+  RemyBatch *b = guard.get();
   b->n_cands = n_cands; b->n_cfgs = n_cfgs; b->n_sims = n_cands * n_cfgs;
   b->has_cands = cands != nullptr;
   b->want_senders = want_senders != 0; b->want_counts = want_use_counts != 0;
   b->sender_stride = sender_stride;
-  b->cfgs.assign(cfgs, cfgs + n_cfgs); b->seeds.assign(seeds, seeds + n_cfgs);
-  if (cands) b->cands.assign(cands, cands + n_cands);
 
   /* ---- tree -> device layout (validated so the kernel cannot walk off the arrays) ---- */
   PreparedTree pt;
@@ -193,24 +239,26 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
       if (cands[c].leaf_index != REMY_NO_OVERRIDE && cands[c].leaf_index >= tree->n_leaves)
         return fail(REMY_EINVAL, "candidate " + std::to_string(c) + " overrides a leaf that does not exist");
   CU(b->bounds.alloc(pt.bounds.size())); CU(b->meta.alloc(pt.meta.size())); CU(b->leaves.alloc(pt.leaves.size()));
+  CU(b->cuts.alloc(pt.cuts.size())); CU(b->table.alloc(pt.table.size()));
   CU(cudaMemcpyAsync(b->bounds.p, pt.bounds.data(), pt.bounds.size() * sizeof(Bounds), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(b->meta.p, pt.meta.data(), pt.meta.size() * sizeof(DevNodeMeta), cudaMemcpyHostToDevice, g_stream));
   CU(cudaMemcpyAsync(b->leaves.p, pt.leaves.data(), pt.leaves.size() * sizeof(DevLeaf), cudaMemcpyHostToDevice, g_stream));
-  CU(b->cuts.alloc(pt.cuts.size())); CU(b->table.alloc(pt.table.size()));
   if (!pt.cuts.empty()) CU(cudaMemcpyAsync(b->cuts.p, pt.cuts.data(), pt.cuts.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   if (!pt.table.empty()) CU(cudaMemcpyAsync(b->table.p, pt.table.data(), pt.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, g_stream));
 
-  /* ---- configs: n_max, ring sizes, cost-sorted order ---- */
+  /* ---- configs: ring sizes, config-sorted order, passes by sender count ---- */
   const BatchPlan plan = plan_batch(cfgs, n_cfgs, n_cands);
-  b->n_max = plan.n_max;
   if (b->want_senders && sender_stride < plan.n_max) return fail(REMY_EINVAL, "sender_stride smaller than the largest num_senders");
-  const uint32_t link_cap = plan.link_cap, delay_cap = plan.delay_cap;
-  const std::vector<uint32_t> &order = plan.order;
+  b->delay_cap = plan.delay_cap;
+  if (plan.passes.size() > MAX_PASSES) return fail(REMY_EINVAL, "internal: too many passes");
 
-  CU(b->d_cfgs.alloc(n_cfgs)); CU(b->d_seeds.alloc(n_cfgs)); CU(b->order.alloc(b->n_sims)); CU(b->work_counter.alloc(1)); CU(b->redo_list.alloc(b->n_sims)); CU(b->redo_count.alloc(1));
-  CU(cudaMemcpyAsync(b->d_cfgs.p, cfgs, n_cfgs * sizeof(RemyNetConfig), cudaMemcpyHostToDevice, g_stream));
-  CU(cudaMemcpyAsync(b->d_seeds.p, seeds, n_cfgs * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
-  CU(cudaMemcpyAsync(b->order.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
+  CU(b->d_cfgs.alloc(n_cfgs)); CU(b->d_seeds.alloc(n_cfgs)); CU(b->order.alloc(b->n_sims));
+  CU(b->redo_list.alloc(b->n_sims)); CU(b->redo_count.alloc(1)); CU(b->redo_counter.alloc(1));
+  if (n_cfgs) {
+    CU(cudaMemcpyAsync(b->d_cfgs.p, cfgs, n_cfgs * sizeof(RemyNetConfig), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(b->d_seeds.p, seeds, n_cfgs * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(b->order.p, plan.order.data(), plan.order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g_stream));
+  }
   if (cands) {
     CU(b->d_cands.alloc(n_cands));
     CU(cudaMemcpyAsync(b->d_cands.p, cands, n_cands * sizeof(RemyLeafOverride), cudaMemcpyHostToDevice, g_stream));
@@ -219,18 +267,36 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   if (b->want_senders) CU(b->out_senders.alloc((size_t)b->n_sims * sender_stride));
   if (b->want_counts) CU(b->out_counts.alloc((size_t)n_cands * b->n_leaves));
 
-  /* ---- launch geometry: persistent blocks, as many as are resident ---- */
-  b->tree_in_smem = smem_bytes(b, true) <= 200 * 1024;
-  b->smem = smem_bytes(b, b->tree_in_smem);
-  const void *kfn = b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
-  CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, SIM_BLOCK, b->smem));
-  if (per_sm < 1) return fail(REMY_ECUDA, "kernel does not fit on an SM");
-  const uint32_t resident = (uint32_t)per_sm * (uint32_t)g_sms;
-  b->grid = std::max(1u, std::min(resident, (b->n_sims + SIM_BLOCK - 1) / SIM_BLOCK));
-  int rc = alloc_scratch(b, b->scratch, b->grid * SIM_BLOCK, link_cap, delay_cap);
-  if (rc) return rc;
+  /* ---- launch geometry: persistent blocks, as many as are resident, per pass ---- */
+  size_t total_bytes = 0;
+  for (const PassPlan &pp : plan.passes) {
+    std::unique_ptr<Pass> ps(new Pass());
+    ps->n_max = pp.n_max; ps->begin = pp.begin; ps->n_work = pp.end - pp.begin;
+    uint32_t resident = 0;
+    int rc = pass_geometry(b, pp.n_max, ps->smem, ps->tree_in_smem, resident);
+    if (rc) return rc;
+    ps->grid = std::max(1u, std::min(resident, (ps->n_work + SIM_BLOCK - 1) / SIM_BLOCK));
+    total_bytes += (size_t)ps->grid * SIM_BLOCK * Scratch::bytes_per_slot(pp.n_max, plan.link_cap, plan.delay_cap, b->want_counts ? b->n_leaves : 0);
+    b->passes.push_back(std::move(ps));
+  }
+  /* keep the working memory within a budget: shrink the first-try link ring if needed
+   * (overflowing simulations are re-run with larger rings) */
+  uint32_t link_cap = plan.link_cap;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = std::min<size_t>(free_b / 2, (size_t)64 << 30);
+  while (total_bytes > budget && link_cap > 1024) {
+    link_cap /= 2;
+    total_bytes = 0;
+    for (auto &ps : b->passes)
+      total_bytes += (size_t)ps->grid * SIM_BLOCK * Scratch::bytes_per_slot(ps->n_max, link_cap, plan.delay_cap, b->want_counts ? b->n_leaves : 0);
+  }
+  for (auto &ps : b->passes) {
+    int rc = alloc_scratch(b, ps->scratch, ps->grid * SIM_BLOCK, ps->n_max, link_cap, plan.delay_cap);
+    if (rc) return rc;
+    CU(ps->counter.alloc(1));
+    CU(cudaEventCreateWithFlags(&ps->done, cudaEventDisableTiming));
+  }
   CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1));
   CU(cudaStreamSynchronize(g_stream));
   *out_batch = guard.release();
@@ -244,15 +310,24 @@ int remy_b200_batch_run(RemyBatch *b, float *kernel_ms)
   CU(cudaSetDevice(g_device));
   b->launches = 0;
   if (b->want_counts) CU(cudaMemsetAsync(b->out_counts.p, 0, b->out_counts.n * sizeof(uint32_t), g_stream));
-  if (kernel_ms) CU(cudaEventRecord(b->ev0, g_stream));
+  CU(cudaEventRecord(b->ev0, g_stream));
   if (b->n_sims) {
-    int rc = launch(b, b->scratch, b->order.p, b->n_sims, b->grid);
-    if (rc) return rc;
+    /* the passes run concurrently on their own streams, largest sender counts first; as a
+     * pass drains, the next one's blocks take over the freed SM resources */
+    for (size_t i = 0; i < b->passes.size(); i++) {
+      Pass &ps = *b->passes[i];
+      cudaStream_t st = g_pass_stream[i];
+      CU(cudaStreamWaitEvent(st, b->ev0, 0));
+      int rc = launch(b, ps.scratch, ps.smem, ps.tree_in_smem, b->order.p + ps.begin, ps.n_work, ps.grid, ps.counter.p, st);
+      if (rc) return rc;
+      CU(cudaEventRecord(ps.done, st));
+      CU(cudaStreamWaitEvent(g_stream, ps.done, 0));
+    }
     /* Simulations whose link queue outgrew the ring are re-run with larger rings, inside
      * the timed region.  (The reference's deque is unbounded; a finite ring is this
      * library's artefact, so it is hidden from the caller as long as memory allows.) */
-    uint32_t cap = b->scratch.link_cap;
-    for (int round = 0; round < 3 && cap < (1u << 24); round++) {
+    uint32_t cap = b->passes.empty() ? 1 : b->passes[0]->scratch.link_cap;
+    for (int round = 0; round < 4 && cap < (1u << 24); round++) {
       CU(cudaMemsetAsync(b->redo_count.p, 0, sizeof(uint32_t), g_stream));
       remy_collect_overflow<<<(b->n_sims + 255) / 256, 256, 0, g_stream>>>(b->out_sims.p, b->n_sims, b->redo_list.p, b->redo_count.p);
       CU(cudaGetLastError());
@@ -262,20 +337,22 @@ int remy_b200_batch_run(RemyBatch *b, float *kernel_ms)
       CU(cudaStreamSynchronize(g_stream));
       if (n_redo == 0) break;
       cap = (uint32_t)std::min<uint64_t>((uint64_t)cap * 16, 1u << 24);
-      const size_t per_slot = (size_t)cap * sizeof(LinkEnt);
-      const size_t budget = (size_t)32 << 30;
-      uint32_t slots = (uint32_t)std::min<size_t>(std::max<size_t>(budget / per_slot, SIM_BLOCK), n_redo);
+      const size_t per_slot = Scratch::bytes_per_slot(REMY_MAX_SENDERS, cap, b->delay_cap, b->want_counts ? b->n_leaves : 0);
+      uint32_t slots = (uint32_t)std::min<size_t>(std::max<size_t>(((size_t)32 << 30) / per_slot, SIM_BLOCK), n_redo);
       slots = ((slots + SIM_BLOCK - 1) / SIM_BLOCK) * SIM_BLOCK;
       Scratch s2;
-      rc = alloc_scratch(b, s2, slots, cap, b->scratch.delay_cap);
+      int rc = alloc_scratch(b, s2, slots, REMY_MAX_SENDERS, cap, b->delay_cap);
       if (rc) return rc;
-      rc = launch(b, s2, b->redo_list.p, n_redo, slots / SIM_BLOCK);
+      size_t smem = 0; bool tis = false; uint32_t resident = 0;
+      rc = pass_geometry(b, REMY_MAX_SENDERS, smem, tis, resident);
+      if (rc) return rc;
+      rc = launch(b, s2, smem, tis, b->redo_list.p, n_redo, slots / SIM_BLOCK, b->redo_counter.p, g_stream);
       if (rc) return rc;
       CU(cudaStreamSynchronize(g_stream)); /* s2 is freed at the end of this scope */
     }
   }
+  CU(cudaEventRecord(b->ev1, g_stream));
   if (kernel_ms) {
-    CU(cudaEventRecord(b->ev1, g_stream));
     CU(cudaEventSynchronize(b->ev1));
     CU(cudaEventElapsedTime(kernel_ms, b->ev0, b->ev1));
   }
@@ -286,17 +363,18 @@ int remy_b200_batch_run(RemyBatch *b, float *kernel_ms)
 int remy_b200_batch_fetch(RemyBatch *b, RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts)
 {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!b || !out_sims) return fail(REMY_EINVAL, "batch/out_sims is NULL");
+  if (!b || (!out_sims && b->n_sims)) return fail(REMY_EINVAL, "batch/out_sims is NULL");
   if (!b->ran) return fail(REMY_EINVAL, "batch has not been run");
   if (out_senders && !b->want_senders) return fail(REMY_EINVAL, "batch was created without want_senders");
   if (out_use_counts && !b->want_counts) return fail(REMY_EINVAL, "batch was created without want_use_counts");
   CU(cudaSetDevice(g_device));
-  CU(cudaMemcpyAsync(out_sims, b->out_sims.p, (size_t)b->n_sims * sizeof(RemySimResult), cudaMemcpyDeviceToHost, g_stream));
+  if (b->n_sims)
+    CU(cudaMemcpyAsync(out_sims, b->out_sims.p, (size_t)b->n_sims * sizeof(RemySimResult), cudaMemcpyDeviceToHost, g_stream));
+  if (out_senders && b->n_sims)
+    CU(cudaMemcpyAsync(out_senders, b->out_senders.p, (size_t)b->n_sims * b->sender_stride * sizeof(RemySenderResult), cudaMemcpyDeviceToHost, g_stream));
+  if (out_use_counts && b->out_counts.n)
+    CU(cudaMemcpyAsync(out_use_counts, b->out_counts.p, b->out_counts.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_stream));
   CU(cudaStreamSynchronize(g_stream));
-  if (out_senders)
-    CU(cudaMemcpy(out_senders, b->out_senders.p, (size_t)b->n_sims * b->sender_stride * sizeof(RemySenderResult), cudaMemcpyDeviceToHost));
-  if (out_use_counts)
-    CU(cudaMemcpy(out_use_counts, b->out_counts.p, b->out_counts.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -306,8 +384,7 @@ void remy_b200_batch_destroy(RemyBatch *b)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!b) return;
-  if (b->ev0) cudaEventDestroy(b->ev0);
-  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (g_stream) cudaStreamSynchronize(g_stream);
   delete b;
 }
 
@@ -317,7 +394,7 @@ int remy_b200_score_batch(const RemyFlatTree *tree,
                           uint32_t sender_stride,
                           RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts)
 {
-  if (!out_sims) return fail(REMY_EINVAL, "out_sims is NULL");
+  if (!out_sims && n_cfgs) return fail(REMY_EINVAL, "out_sims is NULL");
   RemyBatch *b = nullptr;
   int rc = remy_b200_batch_create(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride,
                                   out_senders != nullptr, out_use_counts != nullptr, &b);

@@ -56,6 +56,7 @@
 namespace remy {
 
 constexpr uint32_t LCG_M = 2147483647u;
+constexpr uint32_t INC_BUF = 8; /* buffered sending-time increments per simulation (shared memory) */
 
 struct KernelArgs {
   /* tree (global copies; staged into shared memory when it fits) */
@@ -73,6 +74,7 @@ struct KernelArgs {
   uint32_t *work_counter;
   /* per-slot scratch */
   SenderCold *cold;   uint32_t n_max;      /* [slots][n_max] */
+  double *share;                           /* [slots][n_max] Utility::_tick_share_sending */
   LinkEnt *link_ring; uint32_t link_cap;   /* [slots][link_cap], power of two */
   DelayEnt *delay_ring; uint32_t delay_cap;/* [slots][delay_cap], power of two */
   uint32_t *slot_counts;                   /* [slots][n_leaves] when counting uses */
@@ -237,7 +239,8 @@ __device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int
 /* ------------------------------------------------------------- the sim ---- */
 template <bool COUNT>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
-                        double *hot_share, double *hot_send, /* [s * blockDim.x] strided */
+                        double *inc_buf, double *hot_send, /* shared memory, element i at [i * blockDim.x] */
+                        double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
                         SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
 {
   const uint32_t HS = blockDim.x; /* stride of the shared-memory hot arrays */
@@ -287,7 +290,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     c.packets_sent = 0; c.largest_ack = -1; c.window = 0; c.u_received = 0; c.leaf = 0; c.pad = 0;
     cold[s] = c;
     min_switch = fmin(min_switch, c.next_switch);
-    hot_share[s * HS] = 0.0;
+    share[s] = 0.0;
     hot_send[s * HS] = DBL_MAX;
   }
   if (COUNT) for (uint32_t l = 0; l < A.n_leaves; l++) cnt[l] = 0;
@@ -301,6 +304,22 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   uint32_t dcons = 0, ddeliv = 0, dtail = 0; /* delay ring: [dcons,ddeliv) = Receiver mailbox, [ddeliv,dtail) in flight */
   double dhead_release = DBL_MAX;
   uint64_t iters = 0;
+  /* Sending time is accumulated exactly as the reference does (one rounded addition of
+   * dt/k per sender per tick, sendergang.cc:163-173), but the additions are deferred: the
+   * per-tick increments are identical for every sender that is on, so up to INC_BUF of them
+   * are kept in shared memory and applied, in order, to each such sender at once.  The set
+   * of senders cannot change while increments are buffered (a switch flushes first). */
+  uint32_t ninc = 0, acc_mask = 0;
+  auto flush_share = [&]() {
+    uint32_t am = acc_mask;
+    while (am) {
+      const uint32_t s = __ffs(am) - 1; am &= am - 1;
+      double v = share[s];
+      for (uint32_t k = 0; k < ninc; k++) v = __dadd_rn(v, inc_buf[k * HS]);
+      share[s] = v;
+    }
+    ninc = 0;
+  };
 
   while (t < duration) {
     /* ---- next event (network.cc:75-78) ---- */
@@ -316,6 +335,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
     uint32_t newly_on = 0;
     if (min_switch <= t) {
+      flush_share();
       const uint32_t k0 = __popc(on_mask);
       double ms = DBL_MAX;
       for (uint32_t s = 0; s < n && !err; s++) {
@@ -325,10 +345,10 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           SenderCold c = cold[s];
           bool sending = (on_mask >> s) & 1u;
           double itick = t_prev;       /* SwitchedSender::internal_tick of a sender that was on */
-          double share = hot_share[s * HS];
+          double shr = share[s];
           do {
             if (sending) {             /* switch_off (sendergang.cc:151-161) */
-              if (t > itick) { share = __dadd_rn(share, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
+              if (t > itick) { shr = __dadd_rn(shr, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
               sending = false;
             } else {                   /* switch_on -> Rat::reset (rat.cc:34-48) */
               sending = true;
@@ -351,7 +371,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           } while (nsw <= t);
           c.next_switch = nsw;
           cold[s] = c;
-          hot_share[s * HS] = share;
+          share[s] = shr;
           const uint32_t bit = 1u << s;
           if (sending) {
             on_mask |= bit;
@@ -495,11 +515,10 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     if (advanced) {
       uint32_t am = on_mask & ~newly_on;
       if (am) {
-        const double inc = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
-        while (am) {
-          const uint32_t s = __ffs(am) - 1; am &= am - 1;
-          hot_share[s * HS] = __dadd_rn(hot_share[s * HS], inc);
-        }
+        if (ninc && am != acc_mask) flush_share();
+        acc_mask = am;
+        inc_buf[ninc * HS] = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
+        if (++ninc == INC_BUF) flush_share();
       }
     }
     t_prev = t;
@@ -532,23 +551,24 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   }
 
   /* ---- results: Utility::utility (utility.hh:46-60), SenderGang::utility (sendergang.cc:280-293) ---- */
+  flush_share();
   double total = 0.0;
   uint64_t sent = 0, recv = 0;
   for (uint32_t s = 0; s < n; s++) {
     const SenderCold c = cold[s];
-    const double share = hot_share[s * HS];
+    const double shr = share[s];
     double u;
-    if (share == 0) u = 0.0;
+    if (shr == 0) u = 0.0;
     else if (c.u_received == 0) u = -2147483647.0;
     else {
-      const double tput = __ddiv_rn((double)c.u_received, share);
+      const double tput = __ddiv_rn((double)c.u_received, shr);
       const double del = __ddiv_rn(c.total_delay, (double)c.u_received);
       u = __dsub_rn(log2(tput), log2(__ddiv_rn(del, 100.0)));
     }
     total = __dadd_rn(total, u);
     sent += c.packets_sent; recv += c.u_received;
     if (A.out_senders && s < A.sender_stride) {
-      RemySenderResult r; r.tick_share_sending = share; r.total_delay = c.total_delay;
+      RemySenderResult r; r.tick_share_sending = shr; r.total_delay = c.total_delay;
       r.packets_received = c.u_received; r.packets_sent = c.packets_sent;
       A.out_senders[(size_t)sim * A.sender_stride + s] = r;
     }
@@ -583,13 +603,13 @@ template <bool COUNT>
 __global__ void __launch_bounds__(SIM_BLOCK) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
-  /* layout: [hot_share: n_max*B doubles][hot_send: n_max*B doubles][tree, if staged] */
-  double *hot_share = reinterpret_cast<double *>(smem) + threadIdx.x;
-  double *hot_send = hot_share + (size_t)A.n_max * blockDim.x;
+  /* layout: [inc_buf: INC_BUF*B doubles][hot_send: n_max*B doubles][tree, if staged] */
+  double *inc_buf = reinterpret_cast<double *>(smem) + threadIdx.x;
+  double *hot_send = inc_buf + (size_t)INC_BUF * blockDim.x;
   TreeView T;
   T.axes_mask = A.axes_mask;
   if (A.tree_in_smem) {
-    unsigned char *p = smem + (size_t)2 * A.n_max * blockDim.x * sizeof(double);
+    unsigned char *p = smem + (size_t)(INC_BUF + A.n_max) * blockDim.x * sizeof(double);
     Bounds *sb = reinterpret_cast<Bounds *>(p);
     DevLeaf *sl = reinterpret_cast<DevLeaf *>(sb + (size_t)A.n_nodes * NAX);
     DevNodeMeta *sm = reinterpret_cast<DevNodeMeta *>(sl + A.n_leaves);
@@ -607,13 +627,14 @@ __global__ void __launch_bounds__(SIM_BLOCK) remy_sim_kernel(const KernelArgs A)
   }
   const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   SenderCold *cold = A.cold + slot * A.n_max;
+  double *share = A.share + slot * A.n_max;
   LinkEnt *lring = A.link_ring + slot * A.link_cap;
   DelayEnt *dring = A.delay_ring + slot * A.delay_cap;
   uint32_t *cnt = COUNT ? A.slot_counts + slot * A.n_leaves : nullptr;
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT>(A, T, A.order[w], hot_share, hot_send, cold, lring, dring, cnt);
+    run_sim<COUNT>(A, T, A.order[w], inc_buf, hot_send, share, cold, lring, dring, cnt);
   }
 }
 
