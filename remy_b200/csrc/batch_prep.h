@@ -48,6 +48,7 @@ inline void build_cell_table(PreparedTree &t, uint32_t node)
 {
   DevNodeMeta &md = t.meta[node];
   std::vector<double> cuts[NAX];
+  size_t lo_skip[NAX] = {0}, n_int[NAX] = {0};
   size_t cells = 1;
   for (int a = 0; a < NAX; a++) {
     if (!(t.axes_mask & (1u << a))) continue;
@@ -59,8 +60,17 @@ inline void build_cell_table(PreparedTree &t, uint32_t node)
     }
     std::sort(cuts[a].begin(), cuts[a].end());
     cuts[a].erase(std::unique(cuts[a].begin(), cuts[a].end()), cuts[a].end());
-    if (cuts[a].size() > 255) return;
-    cells *= cuts[a].size() + 1;
+    /* A query that reaches this node lies inside the node's own box (the descent only
+     * enters boxes that contain it), so cuts <= lower always count and cuts >= upper never
+     * do: only the interior cuts need a comparison on the device. */
+    const Bounds &pb = t.bounds[(size_t)node * NAX + a];
+    if (pb.lo != pb.lo || pb.hi != pb.hi) return;
+    size_t lo_n = 0, hi_n = 0;
+    while (lo_n < cuts[a].size() && cuts[a][lo_n] <= pb.lo) lo_n++;
+    while (hi_n < cuts[a].size() - lo_n && cuts[a][cuts[a].size() - 1 - hi_n] >= pb.hi) hi_n++;
+    lo_skip[a] = lo_n; n_int[a] = cuts[a].size() - lo_n - hi_n;
+    if (n_int[a] > 255) return;
+    cells *= n_int[a] + 1;
     if (cells > MAX_TABLE_CELLS) return;
   }
   if (md.count >= NO_CELL_CHILD || t.table.size() + cells > MAX_TABLE_TOTAL) return;
@@ -72,16 +82,17 @@ inline void build_cell_table(PreparedTree &t, uint32_t node)
   md.table_off = (uint32_t)t.table.size();
   md.cuts_off = (uint32_t)t.cuts.size();
   for (int a = 0; a < NAX; a++) {
-    md.ncuts[a] = (uint8_t)cuts[a].size();
-    t.cuts.insert(t.cuts.end(), cuts[a].begin(), cuts[a].end());
+    md.ncuts[a] = (uint8_t)n_int[a];
+    t.cuts.insert(t.cuts.end(), cuts[a].begin() + lo_skip[a], cuts[a].begin() + lo_skip[a] + n_int[a]);
   }
   t.table.resize(t.table.size() + cells, NO_CELL_CHILD);
   std::vector<int> p(NAX, 0);
   for (size_t cell = 0; cell < cells; cell++) {
     size_t rem = cell;
     for (int a = 0; a < NAX; a++) {
-      const size_t dim = (t.axes_mask & (1u << a)) ? cuts[a].size() + 1 : 1;
-      p[a] = (int)(rem % dim); rem /= dim;
+      const size_t dim = (t.axes_mask & (1u << a)) ? n_int[a] + 1 : 1;
+      p[a] = (int)(rem % dim) + (int)lo_skip[a]; /* number of cuts <= m on this axis */
+      rem /= dim;
     }
     for (uint32_t c = 0; c < md.count; c++) {
       bool ok = true;

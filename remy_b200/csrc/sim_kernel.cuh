@@ -518,10 +518,13 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         if (ninc && am != acc_mask) flush_share();
         acc_mask = am;
         inc_buf[ninc * HS] = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
-        if (++ninc == INC_BUF) flush_share();
+        ninc++;
       }
     }
     t_prev = t;
+    /* flush on a fixed iteration phase rather than when the buffer fills: every lane of a
+     * warp then flushes in the same loop iteration (at most INC_BUF increments are pending) */
+    if ((iters & (INC_BUF - 1)) == 0 && ninc) flush_share();
 
     /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
     if (pending && pend_release <= t) {
@@ -600,7 +603,7 @@ constexpr int SIM_BLOCK = 128;
 #ifndef REMY_HOST_EMU
 
 template <bool COUNT>
-__global__ void __launch_bounds__(SIM_BLOCK) remy_sim_kernel(const KernelArgs A)
+__global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   /* layout: [inc_buf: INC_BUF*B doubles][hot_send: n_max*B doubles][tree, if staged] */

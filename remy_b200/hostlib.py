@@ -1,0 +1,144 @@
+"""ctypes view of remy_b200/host/libremy_host.so (the C++ mirror of the reference's
+Evaluator / WhiskerTree / ConfigRange API) for the tests."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+from . import abi
+
+_V = C.c_void_p
+
+
+class HostLib:
+    def __init__(self, path=None):
+        path = path or os.path.join(abi.REPO_ROOT, "remy_b200", "host", "libremy_host.so")
+        self.lib = L = C.CDLL(path)
+        L.remy_host_last_error.restype = C.c_char_p
+        for name in ("remy_host_tree_default", "remy_host_tree_parse", "remy_host_tree_from_flat"):
+            getattr(L, name).restype = _V
+        L.remy_host_tree_parse.argtypes = [C.c_char_p, C.c_size_t]
+        L.remy_host_tree_from_flat.argtypes = [C.POINTER(abi.FlatTreeC)]
+        L.remy_host_tree_free.argtypes = [_V]
+        for name in ("remy_host_tree_serialize", "remy_host_tree_str"):
+            getattr(L, name).restype = C.c_long
+            getattr(L, name).argtypes = [_V, C.c_char_p, C.c_size_t]
+        L.remy_host_tree_flatten.argtypes = [_V, _V, C.c_uint32, _V, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.remy_host_next_generation.restype = C.c_long
+        L.remy_host_next_generation.argtypes = [_V, C.c_uint32, C.c_int, C.c_int, C.c_int, _V, C.c_uint32]
+        L.remy_host_config_range_expand.restype = C.c_long
+        L.remy_host_config_range_expand.argtypes = [C.c_char_p, C.c_size_t, C.c_double, _V, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_long)]
+        L.remy_host_evaluator_score.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.POINTER(C.c_double), _V, C.c_uint32,
+                                                _V, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.remy_host_score_next_generation.restype = C.c_long
+        L.remy_host_score_next_generation.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.c_uint32, _V, C.c_uint32]
+
+    def err(self):
+        return self.lib.remy_host_last_error().decode()
+
+    def _check(self, ok):
+        if not ok:
+            raise RuntimeError(self.err())
+
+    def tree_default(self):
+        return HostTree(self, self.lib.remy_host_tree_default())
+
+    def tree_parse(self, data):
+        h = self.lib.remy_host_tree_parse(data, len(data))
+        self._check(h)
+        return HostTree(self, h)
+
+    def tree_from_flat(self, flat):
+        h = self.lib.remy_host_tree_from_flat(flat.byref())
+        self._check(h)
+        return HostTree(self, h)
+
+    def expand(self, range_bytes, carefulness=1.0):
+        out = np.zeros(1 << 16, dtype=abi.net_config_dtype)
+        dna = C.create_string_buffer(4096)
+        n_dna = C.c_long(0)
+        n = self.lib.remy_host_config_range_expand(range_bytes, len(range_bytes), carefulness, out.ctypes.data, len(out), dna, 4096, C.byref(n_dna))
+        self._check(n >= 0)
+        return out[:n].copy(), dna.raw[:n_dna.value]
+
+
+class HostTree:
+    def __init__(self, host, handle):
+        self.host, self.h = host, handle
+
+    def __del__(self):
+        if self.h:
+            self.host.lib.remy_host_tree_free(self.h)
+            self.h = None
+
+    def _string(self, fn):
+        n = fn(self.h, None, 0)
+        self.host._check(n >= 0)
+        buf = C.create_string_buffer(n + 1)
+        fn(self.h, buf, n)
+        return buf.raw[:n]
+
+    def serialize(self):
+        return self._string(self.host.lib.remy_host_tree_serialize)
+
+    def str(self):
+        return self._string(self.host.lib.remy_host_tree_str).decode()
+
+    def flatten(self):
+        nn, nl = C.c_uint32(0), C.c_uint32(0)
+        self.host._check(self.host.lib.remy_host_tree_flatten(self.h, None, 0, None, 0, C.byref(nn), C.byref(nl)) == 0)
+        nodes = np.zeros(nn.value, dtype=abi.tree_node_dtype)
+        leaves = np.zeros(nl.value, dtype=abi.leaf_action_dtype)
+        self.host._check(self.host.lib.remy_host_tree_flatten(self.h, nodes.ctypes.data, len(nodes), leaves.ctypes.data, len(leaves),
+                                                              C.byref(nn), C.byref(nl)) == 0)
+        return abi.FlatTree(nodes, leaves)
+
+    def next_generation(self, leaf, oi=True, om=True, os_=True):
+        out = np.zeros(512, dtype=abi.leaf_override_dtype)
+        n = self.host.lib.remy_host_next_generation(self.h, leaf, int(oi), int(om), int(os_), out.ctypes.data, len(out))
+        self.host._check(n >= 0)
+        return out[:n].copy()
+
+    def score(self, range_bytes, prng_seed, carefulness=1.0):
+        flat = self.flatten()
+        score = C.c_double(0)
+        counts = np.zeros(flat.n_leaves, dtype=np.uint32)
+        td = np.zeros(1 << 18, dtype=np.float64)
+        n_td = C.c_uint32(0)
+        rc = self.host.lib.remy_host_evaluator_score(self.h, range_bytes, len(range_bytes), prng_seed, carefulness, C.byref(score),
+                                                      counts.ctypes.data, len(counts), td.ctypes.data, len(td), C.byref(n_td))
+        self.host._check(rc == 0)
+        return score.value, counts, td[:n_td.value].reshape(-1, 2).copy()
+
+    def score_next_generation(self, range_bytes, prng_seed, leaf, carefulness=1.0):
+        out = np.zeros(512, dtype=np.float64)
+        n = self.host.lib.remy_host_score_next_generation(self.h, range_bytes, len(range_bytes), prng_seed, carefulness, leaf, out.ctypes.data, len(out))
+        self.host._check(n >= 0)
+        return out[:n].copy()
+
+
+def encode_range(low, high, incr):
+    """RemyBuffers.Range bytes (dna.proto:89-93)."""
+    return b"".join(bytes([0xE9 + 8 * i, 0x03]) + struct.pack("<d", v) for i, v in enumerate((low, high, incr)))
+
+
+def _varint(v):
+    out = b""
+    while v >= 0x80:
+        out += bytes([(v & 0x7F) | 0x80])
+        v >>= 7
+    return out + bytes([v])
+
+
+def encode_config_range(link, rtt, nsrc, buf, off, on, ticks, loss=(0, 0, 0), unicorn=False):
+    """RemyBuffers.ConfigRange (dna.proto:95-104) or, with unicorn=True, the ConfigRangeUnicorn
+    form in which field 77 is a Range (dna.proto:106-119)."""
+    def msg(num, body):
+        return _varint((num << 3) | 2) + _varint(len(body)) + body
+    out = b""
+    for num, r in ((71, link), (72, rtt), (73, nsrc), (74, buf), (75, off), (76, on)):
+        out += msg(num, encode_range(*r))
+    out += msg(77, encode_range(ticks, ticks, 0)) if unicorn else _varint((77 << 3) | 0) + _varint(int(ticks))
+    out += msg(78, encode_range(*loss))
+    return out

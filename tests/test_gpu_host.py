@@ -1,0 +1,73 @@
+"""GPU tests of the C++ host mirror: Evaluator<WhiskerTree>::score and score_candidates (the
+replacement for ActionImprover::evaluate_replacements) against the oracle."""
+import numpy as np
+import pytest
+
+from remy_b200 import abi, hostlib, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def host(built, device):
+    built.build_host()
+    return hostlib.HostLib()
+
+
+def _range(ticks):
+    inf = float(abi.BUFFER_INFINITE)
+    return hostlib.encode_config_range(link=(1, 2, 0.5), rtt=(100, 200, 50), nsrc=(1, 32, 6), buf=(inf, inf, 0),
+                                       off=(5000, 5000, 0), on=(5000, 5000, 0), ticks=ticks)
+
+
+@pytest.mark.parametrize("tree_name", ["default", "RemyCC-2014-100x"])
+def test_evaluator_score_matches_oracle(host, oracle, tree_name):
+    flat = workloads.load_golden_tree(tree_name)
+    tree = host.tree_from_flat(flat)
+    raw = _range(20000)
+    cfgs, _ = host.expand(raw)
+    assert len(cfgs) == 3 * 3 * 6
+    seed = 77
+    score, counts, td = tree.score(raw, seed)
+    seeds = workloads.seeds_for(seed, len(cfgs))
+    sims, snd, want_counts = oracle.score(flat, cfgs, seeds, want_use_counts=True, threads=16)
+    want = 0.0
+    for u in sims["utility"]:
+        want += float(u)                                       # src/evaluator.cc:96
+    assert abs(score - want) <= 1e-9 * abs(want)
+    assert (counts == want_counts[0]).all()
+    k = 0
+    for i, c in enumerate(cfgs):
+        for s in range(int(c["num_senders"])):
+            r = snd[i][s]
+            tput = 0.0 if r["tick_share_sending"] == 0 else float(r["packets_received"]) / r["tick_share_sending"]
+            dly = 0.0 if r["packets_received"] == 0 else r["total_delay"] / float(r["packets_received"])
+            assert td[k][0] == tput and td[k][1] == dly
+            k += 1
+    assert k == len(td)
+    # carefulness scales the run length (src/evaluator.cc:196-201)
+    score2, _, _ = tree.score(raw, seed, carefulness=0.5)
+    cfgs2, _ = host.expand(raw, carefulness=0.5)
+    sims2, _, _ = oracle.score(flat, cfgs2, seeds, want_senders=False, threads=16)
+    assert abs(score2 - float(np.sum(sims2["utility"]))) <= 1e-9 * abs(score2)
+
+
+def test_score_candidates_matches_oracle(host, oracle):
+    """One batch call scores every Whisker::next_generation candidate of a leaf (80 for the
+    default whisker) over all configs, with common random numbers across candidates."""
+    flat = abi.default_tree()
+    tree = host.tree_default()
+    raw = _range(5000)
+    cfgs, _ = host.expand(raw)
+    seed = 5
+    cands = tree.next_generation(0)
+    got = tree.score_next_generation(raw, seed, 0)
+    assert len(got) == len(cands) == 80
+    sims, _, _ = oracle.score(flat, cfgs, workloads.seeds_for(seed, len(cfgs)), cands=cands, want_senders=False, threads=16)
+    want = sims["utility"].reshape(len(cands), len(cfgs))
+    for c in range(len(cands)):
+        w = 0.0
+        for u in want[c]:
+            w += float(u)
+        assert abs(got[c] - w) <= 1e-9 * abs(w), c
+    assert got[0] == tree.score(raw, seed)[0]                  # candidate 0 is the unchanged whisker

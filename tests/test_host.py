@@ -1,0 +1,116 @@
+"""C++ host mirror of the reference API (remy_b200/host): wire formats, candidate generation,
+ConfigRange expansion.  CPU only; the Evaluator calls that need the GPU are in test_gpu_host.py."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from remy_b200 import abi, dna, hostlib, workloads
+
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    built.build_cuda()
+    built.build_host()
+    return hostlib.HostLib()
+
+
+def test_default_tree(host):
+    t = host.tree_default()
+    f = t.flatten()
+    d = abi.default_tree()
+    assert f.nodes.tobytes() == d.nodes.tobytes() and f.leaves.tobytes() == d.leaves.tobytes()
+    # WhiskerTree::str of the default tree (src/whisker.cc:83-89 format; 0/0 uses prints as -nan with glibc)
+    assert t.str().endswith("gen=0 usage=-nan => (win=1 + 1.000000 * win, intersend=3.000000)]")
+    assert host.tree_parse(t.serialize()).flatten().nodes.tobytes() == d.nodes.tobytes()
+
+
+@pytest.mark.parametrize("name", ["RemyCC-2014-100x", "RemyCC-2013-delta1", "RemyCC-2013-delta0.1", "RemyCC-2013-delta10"])
+def test_golden_trees_round_trip(host, name):
+    """flat -> WhiskerTree -> DNA bytes -> WhiskerTree -> flat is the identity, and the python
+    wire reader (remy_b200/dna.py) agrees with the C++ one on those bytes."""
+    flat = workloads.load_golden_tree(name)
+    t = host.tree_from_flat(flat)
+    raw = t.serialize()
+    back = host.tree_parse(raw).flatten()
+    assert back.nodes.tobytes() == flat.nodes.tobytes() and back.leaves.tobytes() == flat.leaves.tobytes()
+    py = dna.flatten(dna.parse_whisker_tree(raw)[0])
+    assert py.nodes.tobytes() == flat.nodes.tobytes() and py.leaves.tobytes() == flat.leaves.tobytes()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not present")
+def test_reference_dna_files_byte_identical(host):
+    for path in sorted(glob.glob(os.path.join(REF, "tests", "*.dna"))):
+        raw = open(path, "rb").read()
+        t = host.tree_parse(raw)
+        assert t.serialize() == raw, path                      # incl. config/optimizer sub-messages and wildcards
+        want = workloads.load_golden_tree(os.path.basename(path)[:-4])
+        got = t.flatten()
+        assert got.nodes.tobytes() == want.nodes.tobytes() and got.leaves.tobytes() == want.leaves.tobytes()
+
+
+def test_next_generation(host):
+    """Whisker::next_generation (src/whisker.cc:46-81) on the default whisker (1, 1.0, 3.0):
+    increment {1,2,0,5,17} x multiple {1,.99,.96,.84} x intersend {3,2.95,2.8,2.2}."""
+    c = host.tree_default().next_generation(0)
+    assert len(c) == 80 and (c["leaf_index"] == 0).all()
+    assert (c[0]["window_increment"], c[0]["window_multiple"], c[0]["intersend"]) == (1, 1.0, 3.0)
+    assert sorted(set(c["window_increment"].tolist())) == [0, 1, 2, 5, 17]
+    rnd = lambda v: (1.0 / 10000.0) * int(10000 * v)      # Whisker::round (src/whisker.cc:91-95)
+    assert sorted(set(c["window_multiple"].tolist())) == sorted(rnd(v) for v in (1 - 0.16, 1 - 0.04, 1 - 0.01, 1.0))
+    assert sorted(set(c["intersend"].tolist())) == sorted(rnd(v) for v in (3 - 0.8, 3 - 0.2, 3 - 0.05, 3.0))
+    assert len(host.tree_default().next_generation(0, True, False, False)) == 5
+    # a leaf of a real tree: every candidate maps back to that leaf
+    t = host.tree_from_flat(workloads.load_golden_tree("RemyCC-2014-100x"))
+    flat = t.flatten()
+    ok = [i for i in range(flat.n_leaves) if 0 <= flat.leaves[i]["window_increment"] <= 256 and 0.25 <= flat.leaves[i]["intersend"] <= 3]
+    g = t.next_generation(ok[0])
+    assert 1 <= len(g) <= 343 and (g["leaf_index"] == ok[0]).all()
+    # the reference aborts on values outside the optimizer's range (src/action.hh:64-67)
+    bad = [i for i in range(flat.n_leaves) if flat.leaves[i]["window_increment"] < 0]
+    if bad:
+        with pytest.raises(RuntimeError, match="Ineligible value"):
+            t.next_generation(bad[0])
+
+
+def test_config_range_expansion(host):
+    """Evaluator::Evaluator(ConfigRange) (src/evaluator.cc:9-38): BASELINE config 2 -> 800 NetConfigs in
+    the reference's nesting order; both wire forms of field 77 are accepted."""
+    inf = float(abi.BUFFER_INFINITE)
+    args = dict(link=(1, 2, 0.25), rtt=(100, 200, 25), nsrc=(1, 32, 1), buf=(inf, inf, 0), off=(5000, 5000, 0),
+                on=(5000, 5000, 0), ticks=100000)
+    want = workloads.default_config_range(ticks=1e5)
+    for unicorn in (False, True):
+        raw = hostlib.encode_config_range(unicorn=unicorn, **args)
+        got, dna_bytes = host.expand(raw)
+        assert len(got) == 800 and got.tobytes() == want.tobytes()
+        assert dna_bytes == hostlib.encode_config_range(unicorn=False, **args)   # ConfigRange::DNA, protoc order
+    got, _ = host.expand(hostlib.encode_config_range(unicorn=False, **args), carefulness=0.1)
+    assert (got["simulation_ticks"] == 10000.0).all()
+    # increments that do not divide the range, and isOne() early exits
+    got, _ = host.expand(hostlib.encode_config_range(link=(1, 2, 0.3), rtt=(150, 150, 10), nsrc=(2, 9, 3), buf=(10, 10, 0),
+                                                     off=(500, 500, 0), on=(5000, 6000, 0), ticks=1000, loss=(0, 0.05, 0.02)))
+    assert len(got) == 4 * 1 * 3 * 1 * 1 * 1 * 3
+    assert got["num_senders"][:9:3].tolist() == [2, 5, 8] and got["buffer_size"][0] == 10
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not present")
+def test_reference_cfg_files(host):
+    """Every file under config/ is a ConfigRangeUnicorn; python and C++ readers agree."""
+    paths = sorted(glob.glob(os.path.join(REF, "config", "*.cfg")))
+    assert len(paths) > 700
+    for path in paths[::7]:
+        raw = open(path, "rb").read()
+        cr = dna.parse_config_range(raw)
+        got, _ = host.expand(raw)
+        if all(cr[k]["low"] == cr[k]["high"] or cr[k]["incr"] == 0 for k in ("link_ppt", "rtt", "num_senders", "buffer_size", "mean_off_duration", "mean_on_duration")):
+            assert len(got) == 1, path
+            g = got[0]
+            assert g["link_ppt"] == cr["link_ppt"]["low"] and g["delay"] == cr["rtt"]["low"]
+            assert g["num_senders"] == int(cr["num_senders"]["low"]) and g["simulation_ticks"] == float(int(cr["simulation_ticks"]["low"]))
+    raw = open(os.path.join(REF, "config", "2_2_really_small_buffer_0.cfg"), "rb").read()
+    g = host.expand(raw)[0][0]
+    assert (g["link_ppt"], g["delay"], g["num_senders"], g["buffer_size"], g["mean_off_duration"], g["simulation_ticks"]) == (2.0, 50.0, 2, 10, 500.0, 600000.0)
