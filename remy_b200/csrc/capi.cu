@@ -58,11 +58,11 @@ template <class T> struct DevBuf {
 
 /* Per-slot working memory of one pass (slot = one resident thread). */
 struct Scratch {
-  DevBuf<SenderCold> cold; DevBuf<double> share; DevBuf<LinkEnt> link; DevBuf<DelayEnt> delay; DevBuf<uint32_t> counts;
+  DevBuf<SenderCold> cold; DevBuf<double> share; DevBuf<double> nsw; DevBuf<LinkEnt> link; DevBuf<DelayEnt> delay; DevBuf<uint32_t> counts;
   uint32_t slots = 0, n_max = 0, link_cap = 0, delay_cap = 0;
   static size_t bytes_per_slot(uint32_t n_max, uint32_t link_cap, uint32_t delay_cap, uint32_t count_leaves)
   {
-    return (size_t)n_max * (sizeof(SenderCold) + sizeof(double)) + (size_t)link_cap * sizeof(LinkEnt)
+    return (size_t)n_max * (sizeof(SenderCold) + 2 * sizeof(double)) + (size_t)link_cap * sizeof(LinkEnt)
            + (size_t)delay_cap * sizeof(DelayEnt) + (size_t)count_leaves * sizeof(uint32_t);
   }
 };
@@ -119,7 +119,7 @@ KernelArgs make_args(RemyBatch *b, const Scratch &s, bool tree_in_smem, const ui
   a.n_nodes = b->n_nodes; a.n_leaves = b->n_leaves; a.axes_mask = b->axes_mask; a.tree_in_smem = tree_in_smem;
   a.cands = b->has_cands ? b->d_cands.p : nullptr; a.cfgs = b->d_cfgs.p; a.seeds = b->d_seeds.p;
   a.order = order; a.n_cfgs = b->n_cfgs; a.n_work = n_work; a.work_counter = counter;
-  a.cold = s.cold.p; a.share = s.share.p; a.n_max = s.n_max; a.link_ring = s.link.p; a.link_cap = s.link_cap;
+  a.cold = s.cold.p; a.share = s.share.p; a.nsw = s.nsw.p; a.n_max = s.n_max; a.link_ring = s.link.p; a.link_cap = s.link_cap;
   a.delay_ring = s.delay.p; a.delay_cap = s.delay_cap; a.slot_counts = s.counts.p;
   a.out_sims = b->out_sims.p; a.out_senders = b->want_senders ? b->out_senders.p : nullptr;
   a.sender_stride = b->sender_stride; a.out_use_counts = b->want_counts ? b->out_counts.p : nullptr;
@@ -131,6 +131,7 @@ int alloc_scratch(RemyBatch *b, Scratch &s, uint32_t slots, uint32_t n_max, uint
   s.slots = slots; s.n_max = n_max; s.link_cap = link_cap; s.delay_cap = delay_cap;
   CU(s.cold.alloc((size_t)slots * n_max));
   CU(s.share.alloc((size_t)slots * n_max));
+  CU(s.nsw.alloc((size_t)slots * n_max));
   CU(s.link.alloc((size_t)slots * link_cap));
   CU(s.delay.alloc((size_t)slots * delay_cap));
   if (b->want_counts) CU(s.counts.alloc((size_t)slots * b->n_leaves));

@@ -26,15 +26,16 @@ struct REMY_ALIGN(16) SenderCold {
   double last_tick_received;
   double min_rtt;
   double total_delay;       /* Utility::_total_delay */
+  double reserved;
+  uint32_t leaf;            /* leaf returned by the sender's latest lookup */
+  uint32_t pad;
+  /* bytes 96..127: everything a transmission reads or writes, in one 32-byte sector */
   double last_send_time;    /* Rat::_last_send_time */
   double intersend;         /* Rat::_intersend_time */
-  double next_switch;       /* SwitchedSender::next_switch_tick */
   uint32_t packets_sent;    /* Rat::_packets_sent */
   int32_t largest_ack;      /* Rat::_largest_ack */
   int32_t window;           /* Rat::_the_window */
   uint32_t u_received;      /* Utility::_packets_received */
-  uint32_t leaf;            /* leaf returned by the sender's latest lookup */
-  uint32_t pad;
 };
 static_assert(sizeof(SenderCold) == 128, "SenderCold must be one 128-byte line");
 

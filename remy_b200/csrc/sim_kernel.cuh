@@ -56,6 +56,9 @@
 namespace remy {
 
 constexpr uint32_t LCG_M = 2147483647u;
+#ifndef REMY_ACK_GATE
+#define REMY_ACK_GATE 0 /* max iterations a lane with mail waits for its warp; 0 disables the gate (measured: -15% on B200) */
+#endif
 constexpr uint32_t INC_BUF = 8; /* buffered sending-time increments per simulation (shared memory) */
 
 struct KernelArgs {
@@ -75,6 +78,7 @@ struct KernelArgs {
   /* per-slot scratch */
   SenderCold *cold;   uint32_t n_max;      /* [slots][n_max] */
   double *share;                           /* [slots][n_max] Utility::_tick_share_sending */
+  double *nsw;                             /* [slots][n_max] SwitchedSender::next_switch_tick */
   LinkEnt *link_ring; uint32_t link_cap;   /* [slots][link_cap], power of two */
   DelayEnt *delay_ring; uint32_t delay_cap;/* [slots][delay_cap], power of two */
   uint32_t *slot_counts;                   /* [slots][n_leaves] when counting uses */
@@ -83,6 +87,19 @@ struct KernelArgs {
   RemySenderResult *out_senders; uint32_t sender_stride; /* optional */
   uint32_t *out_use_counts;                /* [n_cands][n_leaves], optional */
 };
+
+/* Non-binding request to bring the line holding p towards the SM (HBM/L2 latency of the
+ * next ack's state is the kernel's main stall; the address is known ticks in advance). */
+__device__ __forceinline__ void prefetch_line(const void *p)
+{
+#if defined(REMY_HOST_EMU) || (defined(REMY_PREFETCH) && REMY_PREFETCH == 0)
+  (void)p;
+#elif defined(REMY_PREFETCH) && REMY_PREFETCH == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 
 /* ---------------------------------------------------------------- PRNG ---- */
 /* minstd_rand0 step (bits/random.h:1592, 368-372): 16807 x mod (2^31-1) via the
@@ -135,15 +152,24 @@ __device__ __forceinline__ uint32_t uniform_int(uint32_t &x, uint32_t u)
 constexpr uint32_t SHUFFLE_SAFE = 2147483645u - 1122u;
 
 /* Advance the PRNG by exactly the draws std::shuffle makes for n elements
- * (bits/stl_algo.h:3742-3805) without building the permutation. */
+ * (bits/stl_algo.h:3742-3805) without building the permutation.
+ *
+ * Fast path: the n/2 LCG steps run on a lazily reduced residue (x' = lo31 + hi is congruent
+ * to 16807 x mod m but may be >= m; it stays < 2^31 + 2^15, so the next product still fits
+ * in 46 bits).  uniform_int can only reject a draw that lies in the top ~1122 values of the
+ * range; the running max of the lazily reduced residues over-approximates that (a residue
+ * >= m looks large but is really small), so a suspicious tick (p ~ 1e-5) takes the exact path. */
 __device__ __forceinline__ uint32_t shuffle_skip(uint32_t x, uint32_t n)
 {
   const uint32_t x0 = x;
   const uint32_t draws = n >> 1;
   uint32_t mx = 0;
-  for (uint32_t j = 0; j < draws; j++) { x = lcg_next(x); mx = max(mx, x); }
-  if (mx - 1u < SHUFFLE_SAFE) return x;
-  /* a draw landed within ~1e-6 of the top of the range: redo exactly */
+  for (uint32_t j = 0; j < draws; j++) {
+    const uint64_t p = (uint64_t)x * 16807u;
+    x = (uint32_t)(p & 0x7fffffffu) + (uint32_t)(p >> 31);
+    mx = max(mx, x);
+  }
+  if (mx - 1u < SHUFFLE_SAFE) return x; /* every residue was canonical (< m) and none rejectable */
   x = x0;
   uint32_t i = 1;
   if ((n & 1u) == 0) { (void)uniform_int(x, 1); i = 2; }
@@ -209,9 +235,14 @@ __device__ __forceinline__ uint32_t find_leaf(const TreeView &T, const double *m
       for (int a = 0; a < NAX; a++) {
         if (T.axes_mask & (1u << a)) {
           const uint32_t nc = md.ncuts[a];
-          uint32_t p = 0;
-          for (uint32_t k = 0; k < nc; k++) p += (m[a] >= cp[k]) ? 1u : 0u;
-          idx += p * stride; stride *= nc + 1; cp += nc;
+          if (nc == 1) { /* a bisected axis */
+            if (m[a] >= cp[0]) idx += stride;
+            stride += stride; cp++;
+          } else if (nc) {
+            uint32_t p = 0;
+            for (uint32_t k = 0; k < nc; k++) p += (m[a] >= cp[k]) ? 1u : 0u;
+            idx += p * stride; stride *= nc + 1; cp += nc;
+          }
         }
       }
       const uint32_t c = T.table[md.table_off + idx];
@@ -241,6 +272,7 @@ template <bool COUNT>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         double *inc_buf, double *hot_send, /* shared memory, element i at [i * blockDim.x] */
                         double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
+                        double *nsw,                        /* [n_max] SwitchedSender::next_switch_tick, HBM */
                         SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
 {
   const uint32_t HS = blockDim.x; /* stride of the shared-memory hot arrays */
@@ -286,10 +318,12 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     for (int a = 0; a < NAX; a++) c.mem[a] = 0;
     c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0; c.total_delay = 0;
     c.last_send_time = 0; c.intersend = 0;
-    c.next_switch = exp_sample(prng, start_rate);
+    c.reserved = 0;
+    const double first_switch = exp_sample(prng, start_rate);
+    nsw[s] = first_switch;
     c.packets_sent = 0; c.largest_ack = -1; c.window = 0; c.u_received = 0; c.leaf = 0; c.pad = 0;
     cold[s] = c;
-    min_switch = fmin(min_switch, c.next_switch);
+    min_switch = fmin(min_switch, first_switch);
     share[s] = 0.0;
     hot_send[s * HS] = DBL_MAX;
   }
@@ -302,7 +336,13 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   double pend_release = 0, pend_sent = 0; uint32_t pend_seq = 0, pend_src = 0;
   uint32_t lhead = 0, ltail = 0;       /* Link::_buffer ring */
   uint32_t dcons = 0, ddeliv = 0, dtail = 0; /* delay ring: [dcons,ddeliv) = Receiver mailbox, [ddeliv,dtail) in flight */
-  double dhead_release = DBL_MAX;
+  /* the oldest in-flight delay entry and the (single) delivered-but-unread one are kept in
+   * registers: the ring is only read when an entry becomes the head */
+  double dhead_release = DBL_MAX, dh_sent = 0; uint32_t dh_seq = 0, dh_src = 0;
+  /* ... and so is the entry behind it (valid when dtail - ddeliv >= 2), so that the HBM read of
+   * a delay-ring entry is issued a whole service time before its first use */
+  double dn_release = 0, dn_sent = 0; uint32_t dn_seq = 0, dn_src = 0;
+  double m_sent = 0; uint32_t m_seq = 0, m_src = 0;
   uint64_t iters = 0;
   /* Sending time is accumulated exactly as the reference does (one rounded addition of
    * dt/k per sender per tick, sendergang.cc:163-173), but the additions are deferred: the
@@ -321,7 +361,26 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     ninc = 0;
   };
 
+  uint32_t waited = 0;
   while (t < duration) {
+#if REMY_ACK_GATE
+    /* Warp-level phase alignment.  A tick that starts with mail (ack -> Memory update -> tree
+     * lookup -> usually a transmission) is several times heavier than a plain tick, and in any
+     * given loop iteration only a fraction of a warp's lanes is at that point, so the heavy code
+     * would run with few active lanes every iteration.  Lanes with mail therefore idle until at
+     * least half of the warp's running lanes have mail too (or they have waited two iterations):
+     * the heavy path then runs once, nearly converged.  Neighbouring lanes run the same config
+     * (the work list is sorted by config), hence the same link/delay period, and stay aligned.
+     * Idling does not touch simulation state, so results are unchanged. */
+    {
+      const bool mail = dcons != ddeliv;
+      const unsigned act = __activemask();
+      const unsigned mm = __ballot_sync(act, mail);
+      const unsigned late = __ballot_sync(act, mail && waited >= REMY_ACK_GATE);
+      if (mail && !late && 2 * __popc(mm) < __popc(act)) { waited++; continue; }
+      waited = 0;
+    }
+#endif
     /* ---- next event (network.cc:75-78) ---- */
     double tn = fmax(t, fmin(min_switch, next_send)); /* SenderGang::next_event_time */
     if (pending) tn = fmin(tn, pend_release);           /* Link::next_event_time */
@@ -334,14 +393,16 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
 
     /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
     uint32_t newly_on = 0;
+    bool sends_dirty = false; /* a window or pacing deadline changed in this tick */
     if (min_switch <= t) {
+      sends_dirty = true;
       flush_share();
       const uint32_t k0 = __popc(on_mask);
       double ms = DBL_MAX;
       for (uint32_t s = 0; s < n && !err; s++) {
-        double nsw = cold[s].next_switch;
-        if (nsw <= t) {
-          if (nsw != t) err |= REMY_ERR_ASSERT;
+        double nx = nsw[s];
+        if (nx <= t) {
+          if (nx != t) err |= REMY_ERR_ASSERT;
           SenderCold c = cold[s];
           bool sending = (on_mask >> s) & 1u;
           double itick = t_prev;       /* SwitchedSender::internal_tick of a sender that was on */
@@ -367,9 +428,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
               c.leaf = leaf;
               itick = t;
             }
-            nsw = __dadd_rn(nsw, exp_sample(prng, sending ? stop_rate : start_rate));
-          } while (nsw <= t);
-          c.next_switch = nsw;
+            nx = __dadd_rn(nx, exp_sample(prng, sending ? stop_rate : start_rate));
+          } while (nx <= t);
+          nsw[s] = nx;
           cold[s] = c;
           share[s] = shr;
           const uint32_t bit = 1u << s;
@@ -386,7 +447,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             if (COUNT) zero_mask &= ~bit;
           }
         }
-        ms = fmin(ms, nsw);
+        ms = fmin(ms, nx);
       }
       min_switch = ms;
       if (err) break;
@@ -398,17 +459,24 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     prng = shuffle_skip(prng, n);
 
     /* ---- 3. receive_feedback for every mailbox (sendergang.cc:175-188) ---- */
+    /* the sender acked in this tick usually transmits in this tick: its send state is handed
+     * over in registers instead of being re-read from HBM */
+    uint32_t ak_s = 0xFFFFFFFFu, ak_seq = 0; int32_t ak_lim = 0; double ak_isend = 0;
     if (dcons != ddeliv) {
+      sends_dirty = true;
       uint32_t done = 0;
+      const bool single = (ddeliv - dcons) == 1; /* the usual case: its fields are in m_* */
       for (uint32_t i = dcons; i != ddeliv && !err; i++) {
-        const uint32_t s = dring[i & dmask].src;
+        const uint32_t s = single ? m_src : dring[i & dmask].src;
         if ((done >> s) & 1u) continue;
         done |= 1u << s;
         SenderCold c = cold[s];
         const int32_t old_ack = c.largest_ack;
         int32_t last_seq = 0;
         for (uint32_t j = i; j != ddeliv; j++) {
-          const DelayEnt e = dring[j & dmask];
+          DelayEnt e;
+          if (single) { e.tick_sent = m_sent; e.seq = m_seq; e.src = m_src; }
+          else e = dring[j & dmask];
           if (e.src != s) continue;
           /* Utility::packets_received (utility.hh:20-27) */
           const double rtt = __dsub_rn(t, e.tick_sent);
@@ -446,6 +514,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         c.intersend = w.intersend;
         c.leaf = leaf;
         cold[s] = c;
+        ak_s = s; ak_seq = c.packets_sent; ak_lim = c.largest_ack + 1 + c.window; ak_isend = c.intersend;
         const uint32_t bit = 1u << s;
         if (on_mask & bit) {
           const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
@@ -466,15 +535,16 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       while (zm) { const uint32_t s = __ffs(zm) - 1; zm &= zm - 1; cnt[cold[s].leaf]++; }
     }
 
-    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34) ---- */
-    {
-      uint32_t ready = 0;
+    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34) ----
+     * (the scan is skipped when no deadline is due and nothing changed: next_send stays valid) */
+    if (sends_dirty || next_send <= t) {
+      uint32_t ready = 0, ns_sender = 0xFFFFFFFFu;
       double ns = DBL_MAX;
       uint32_t om = open_mask;
       while (om) {
         const uint32_t s = __ffs(om) - 1; om &= om - 1;
         const double st = hot_send[s * HS];
-        if (st <= t) ready |= 1u << s; else ns = fmin(ns, st);
+        if (st <= t) ready |= 1u << s; else if (st < ns) { ns = st; ns_sender = s; }
       }
       if (ready) {
         uint8_t perm[REMY_MAX_SENDERS];
@@ -487,9 +557,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           else s = __ffs(left) - 1;
           left &= ~(1u << s);
           SenderCold *c = &cold[s];
-          const uint32_t seq = c->packets_sent;
-          const int32_t lim = c->largest_ack + 1 + c->window;
-          const double isend = c->intersend;
+          uint32_t seq; int32_t lim; double isend;
+          if (s == ak_s) { seq = ak_seq; lim = ak_lim; isend = ak_isend; ak_seq = seq + 1; }
+          else { seq = c->packets_sent; lim = c->largest_ack + 1 + c->window; isend = c->intersend; }
           c->packets_sent = seq + 1;
           c->last_send_time = t;
           /* Link::accept (link.hh:26-34) */
@@ -504,11 +574,12 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           const double st = open ? __dadd_rn(t, isend) : DBL_MAX;
           hot_send[s * HS] = st;
           if (!open) open_mask &= ~(1u << s);
-          ns = fmin(ns, st);
+          if (st < ns) { ns = st; ns_sender = s; }
         }
         if (err) break;
       }
       next_send = ns;
+      if (ns_sender != 0xFFFFFFFFu) prefetch_line(&cold[ns_sender].intersend); /* the sector its send will read */
     }
 
     /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) ---- */
@@ -525,6 +596,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     /* flush on a fixed iteration phase rather than when the buffer fills: every lane of a
      * warp then flushes in the same loop iteration (at most INC_BUF increments are pending) */
     if ((iters & (INC_BUF - 1)) == 0 && ninc) flush_share();
+    else if ((iters & (INC_BUF - 1)) == INC_BUF - 1 && ninc) { /* next iteration flushes: start fetching the sums */
+      for (uint32_t s0 = 0; s0 < n; s0 += 16) prefetch_line(&share[s0]);
+    }
 
     /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
     if (pending && pend_release <= t) {
@@ -536,20 +610,34 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         if (dtail - dcons >= A.delay_cap) { err |= REMY_ERR_DELAY_OVERFLOW; break; }
         DelayEnt e; e.release = __dadd_rn(t, delay); e.tick_sent = pend_sent; e.seq = pend_seq; e.src = pend_src; e.pad[0] = 0; e.pad[1] = 0;
         dring[dtail & dmask] = e;
-        if (ddeliv == dtail) dhead_release = e.release;
+        if (ddeliv == dtail) { /* it is the head of the delay line right away */
+          dhead_release = e.release; dh_sent = e.tick_sent; dh_seq = e.seq; dh_src = e.src;
+        } else if (dtail - ddeliv == 1) { /* ... or the entry right behind the head */
+          dn_release = e.release; dn_sent = e.tick_sent; dn_seq = e.seq; dn_src = e.src;
+        }
         dtail++;
       }
       pending = false;
     }
     if (!pending && lhead != ltail) {
       const LinkEnt e = lring[lhead & lmask]; lhead++;
+      if ((lhead & 7u) == 0 && (ltail - lhead) > 8) prefetch_line(&lring[(lhead + 8) & lmask]); /* next 128-byte line of the queue */
       pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
     }
     /* ---- 7. Delay::tick (delay.hh:53-63) -> Receiver::accept ---- */
     while (ddeliv != dtail && dhead_release <= t) {
       if (dhead_release != t) err |= REMY_ERR_ASSERT;
+      /* Receiver::accept: the delivered packet's fields move to the mail registers */
+      m_sent = dh_sent; m_seq = dh_seq; m_src = dh_src;
       ddeliv++;
-      if (ddeliv != dtail) dhead_release = dring[ddeliv & dmask].release;
+      if (ddeliv != dtail) {
+        dhead_release = dn_release; dh_sent = dn_sent; dh_seq = dn_seq; dh_src = dn_src;
+        if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
+          const DelayEnt h = dring[(ddeliv + 1) & dmask];
+          dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
+          if (((ddeliv + 1) & 3u) == 3u && (dtail - ddeliv) > 6) prefetch_line(&dring[(ddeliv + 5) & dmask]);
+        }
+      }
     }
   }
 
@@ -631,13 +719,14 @@ __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs
   const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   SenderCold *cold = A.cold + slot * A.n_max;
   double *share = A.share + slot * A.n_max;
+  double *nsw = A.nsw + slot * A.n_max;
   LinkEnt *lring = A.link_ring + slot * A.link_cap;
   DelayEnt *dring = A.delay_ring + slot * A.delay_cap;
   uint32_t *cnt = COUNT ? A.slot_counts + slot * A.n_leaves : nullptr;
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT>(A, T, A.order[w], inc_buf, hot_send, share, cold, lring, dring, cnt);
+    run_sim<COUNT>(A, T, A.order[w], inc_buf, hot_send, share, nsw, cold, lring, dring, cnt);
   }
 }
 

@@ -29,7 +29,7 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
   std::vector<SenderCold> cold(plan.n_max);
   std::vector<DelayEnt> dring(plan.delay_cap);
   std::vector<uint32_t> cnt(tree->n_leaves);
-  std::vector<double> hot(INC_BUF + plan.n_max), share(plan.n_max);
+  std::vector<double> hot(INC_BUF + plan.n_max), share(plan.n_max), nsw(plan.n_max);
   if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * (size_t)n_cands * tree->n_leaves);
   uint32_t cap = plan.link_cap;
   std::vector<uint32_t> todo = plan.order;
@@ -46,8 +46,8 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
     TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
     std::vector<uint32_t> redo;
     for (uint32_t sim : todo) {
-      if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, share.data(), cold.data(), lring.data(), dring.data(), cnt.data());
-      else run_sim<false>(A, T, sim, hot.data(), hot.data() + INC_BUF, share.data(), cold.data(), lring.data(), dring.data(), nullptr);
+      if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, share.data(), nsw.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+      else run_sim<false>(A, T, sim, hot.data(), hot.data() + INC_BUF, share.data(), nsw.data(), cold.data(), lring.data(), dring.data(), nullptr);
       if (out_sims[sim].error & REMY_ERR_LINK_OVERFLOW) redo.push_back(sim);
     }
     todo.swap(redo);
