@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ticks", type=float, default=1e5, help="simulation_ticks per NetConfig")
-    ap.add_argument("--replicas", type=int, default=128, help="evaluator seeds per GPU (x 800 NetConfigs)")
+    ap.add_argument("--replicas", type=int, default=192, help="evaluator seeds per GPU (x 800 NetConfigs)")
     ap.add_argument("--tree", default="RemyCC-2014-100x")
     ap.add_argument("--cpu-stride", type=int, default=4)
     args = ap.parse_args()

@@ -51,6 +51,11 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 template <class T> struct DevBuf {
   T *p = nullptr; size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
   cudaError_t alloc(size_t count) { free(); n = count; if (!count) return cudaSuccess; return cudaMalloc(&p, count * sizeof(T)); }
   void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DevBuf() { free(); }
@@ -58,11 +63,14 @@ template <class T> struct DevBuf {
 
 /* Per-slot working memory of one pass (slot = one resident thread). */
 struct Scratch {
-  DevBuf<SenderCold> cold; DevBuf<double> share; DevBuf<double> nsw; DevBuf<LinkEnt> link; DevBuf<DelayEnt> delay; DevBuf<uint32_t> counts;
-  uint32_t slots = 0, n_max = 0, link_cap = 0, delay_cap = 0;
+  DevBuf<SenderCold> cold; DevBuf<double> share; DevBuf<double> nsw; DevBuf<SendState> sendst; DevBuf<LinkEnt> link; DevBuf<DelayEnt> delay; DevBuf<uint32_t> counts;
+  uint32_t slots = 0, n_max = 0, link_cap = 0, delay_cap = 0, count_leaves = 0;
+  Scratch() {}
+  Scratch(Scratch &&) = default;
+  Scratch &operator=(Scratch &&) = default;
   static size_t bytes_per_slot(uint32_t n_max, uint32_t link_cap, uint32_t delay_cap, uint32_t count_leaves)
   {
-    return (size_t)n_max * (sizeof(SenderCold) + 2 * sizeof(double)) + (size_t)link_cap * sizeof(LinkEnt)
+    return (size_t)n_max * (sizeof(SenderCold) + 2 * sizeof(double) + sizeof(SendState)) + (size_t)link_cap * sizeof(LinkEnt)
            + (size_t)delay_cap * sizeof(DelayEnt) + (size_t)count_leaves * sizeof(uint32_t);
   }
 };
@@ -103,7 +111,7 @@ namespace {
 
 size_t smem_bytes(const RemyBatch *b, uint32_t n_max, bool with_tree)
 {
-  return (size_t)(INC_BUF + n_max) * SIM_BLOCK * sizeof(double) + (with_tree ? b->tree_bytes : 0);
+  return (REMY_HOT_LOCAL ? 0 : (size_t)(INC_BUF + n_max) * SIM_BLOCK * sizeof(double)) + (with_tree ? b->tree_bytes : 0);
 }
 
 const void *kernel_fn(const RemyBatch *b)
@@ -119,23 +127,53 @@ KernelArgs make_args(RemyBatch *b, const Scratch &s, bool tree_in_smem, const ui
   a.n_nodes = b->n_nodes; a.n_leaves = b->n_leaves; a.axes_mask = b->axes_mask; a.tree_in_smem = tree_in_smem;
   a.cands = b->has_cands ? b->d_cands.p : nullptr; a.cfgs = b->d_cfgs.p; a.seeds = b->d_seeds.p;
   a.order = order; a.n_cfgs = b->n_cfgs; a.n_work = n_work; a.work_counter = counter;
-  a.cold = s.cold.p; a.share = s.share.p; a.nsw = s.nsw.p; a.n_max = s.n_max; a.link_ring = s.link.p; a.link_cap = s.link_cap;
+  a.cold = s.cold.p; a.share = s.share.p; a.nsw = s.nsw.p; a.sendst = s.sendst.p; a.n_max = s.n_max; a.link_ring = s.link.p; a.link_cap = s.link_cap;
   a.delay_ring = s.delay.p; a.delay_cap = s.delay_cap; a.slot_counts = s.counts.p;
   a.out_sims = b->out_sims.p; a.out_senders = b->want_senders ? b->out_senders.p : nullptr;
   a.sender_stride = b->sender_stride; a.out_use_counts = b->want_counts ? b->out_counts.p : nullptr;
   return a;
 }
 
+/* Working memory of destroyed batches is kept for the next batch of the same geometry (an
+ * Evaluator scores batch after batch of identical shape; cudaMalloc/cudaFree of tens of GB
+ * would otherwise sit inside every one-shot call). */
+std::vector<Scratch> g_scratch_pool;
+constexpr size_t SCRATCH_POOL_MAX = 4; /* one batch's worth of passes */
+
+void recycle_scratch(Scratch &&s)
+{
+  if (!s.cold.p) return;
+  if (g_scratch_pool.size() >= SCRATCH_POOL_MAX) g_scratch_pool.erase(g_scratch_pool.begin());
+  g_scratch_pool.push_back(std::move(s));
+}
+
 int alloc_scratch(RemyBatch *b, Scratch &s, uint32_t slots, uint32_t n_max, uint32_t link_cap, uint32_t delay_cap)
 {
-  s.slots = slots; s.n_max = n_max; s.link_cap = link_cap; s.delay_cap = delay_cap;
-  CU(s.cold.alloc((size_t)slots * n_max));
-  CU(s.share.alloc((size_t)slots * n_max));
-  CU(s.nsw.alloc((size_t)slots * n_max));
-  CU(s.link.alloc((size_t)slots * link_cap));
-  CU(s.delay.alloc((size_t)slots * delay_cap));
-  if (b->want_counts) CU(s.counts.alloc((size_t)slots * b->n_leaves));
-  return 0;
+  const uint32_t count_leaves = b->want_counts ? b->n_leaves : 0;
+  for (size_t i = 0; i < g_scratch_pool.size(); i++) {
+    Scratch &c = g_scratch_pool[i];
+    if (c.slots == slots && c.n_max == n_max && c.link_cap == link_cap && c.delay_cap == delay_cap && c.count_leaves == count_leaves) {
+      s = std::move(c);
+      g_scratch_pool.erase(g_scratch_pool.begin() + i);
+      return 0;
+    }
+  }
+  s.slots = slots; s.n_max = n_max; s.link_cap = link_cap; s.delay_cap = delay_cap; s.count_leaves = count_leaves;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    cudaError_t e = s.cold.alloc((size_t)slots * n_max);
+    if (e == cudaSuccess) e = s.share.alloc((size_t)slots * n_max);
+    if (e == cudaSuccess) e = s.nsw.alloc((size_t)slots * n_max);
+    if (e == cudaSuccess) e = s.sendst.alloc((size_t)slots * n_max);
+    if (e == cudaSuccess) e = s.link.alloc((size_t)slots * link_cap);
+    if (e == cudaSuccess) e = s.delay.alloc((size_t)slots * delay_cap);
+    if (e == cudaSuccess && count_leaves) e = s.counts.alloc((size_t)slots * count_leaves);
+    if (e == cudaSuccess) return 0;
+    cudaGetLastError();
+    s.cold.free(); s.share.free(); s.nsw.free(); s.sendst.free(); s.link.free(); s.delay.free(); s.counts.free();
+    if (attempt == 0 && !g_scratch_pool.empty()) { g_scratch_pool.clear(); continue; } /* give pooled memory back and retry */
+    return fail(REMY_ENOMEM, std::string("scratch allocation failed: ") + cudaGetErrorString(e));
+  }
+  return fail(REMY_ENOMEM, "scratch allocation failed");
 }
 
 /* Shared memory and residency of the kernel for a pass that accepts up to n_max senders. */
@@ -200,6 +238,7 @@ int remy_b200_init(int device)
 void remy_b200_shutdown(void)
 {
   std::lock_guard<std::mutex> lk(g_mu);
+  g_scratch_pool.clear();
   if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   for (int i = 0; i < MAX_PASSES; i++)
     if (g_pass_stream[i]) { cudaStreamDestroy(g_pass_stream[i]); g_pass_stream[i] = nullptr; }
@@ -386,6 +425,7 @@ void remy_b200_batch_destroy(RemyBatch *b)
   std::lock_guard<std::mutex> lk(g_mu);
   if (!b) return;
   if (g_stream) cudaStreamSynchronize(g_stream);
+  for (auto &p : b->passes) recycle_scratch(std::move(p->scratch));
   delete b;
 }
 

@@ -39,6 +39,12 @@ struct REMY_ALIGN(16) SenderCold {
 };
 static_assert(sizeof(SenderCold) == 128, "SenderCold must be one 128-byte line");
 
+/* What Rat::send needs (reference src/rat-templates.cc:20-34), mirrored out of SenderCold into a
+ * 16-byte record: 0.5 KB per simulation, so this array stays L2-resident while the 128-byte cold
+ * lines (4 KB per simulation) stream through HBM. */
+struct REMY_ALIGN(16) SendState { uint32_t packets_sent; int32_t lim; double intersend; };
+static_assert(sizeof(SendState) == 16, "SendState layout");
+
 /* Link::_buffer entry and Delay::_queue entry (reference src/link.hh:15, src/delay.hh:16);
  * flow_id and tick_received are not stored: the first is dead on the Rat path, the second
  * is the tick at which the entry is consumed. */

@@ -56,6 +56,9 @@
 namespace remy {
 
 constexpr uint32_t LCG_M = 2147483647u;
+#ifndef REMY_HOT_LOCAL
+#define REMY_HOT_LOCAL 0
+#endif
 #ifndef REMY_ACK_GATE
 #define REMY_ACK_GATE 0 /* max iterations a lane with mail waits for its warp; 0 disables the gate (measured: -15% on B200) */
 #endif
@@ -79,6 +82,7 @@ struct KernelArgs {
   SenderCold *cold;   uint32_t n_max;      /* [slots][n_max] */
   double *share;                           /* [slots][n_max] Utility::_tick_share_sending */
   double *nsw;                             /* [slots][n_max] SwitchedSender::next_switch_tick */
+  SendState *sendst;                       /* [slots][n_max] what a transmission needs, compact enough to stay in L2 */
   LinkEnt *link_ring; uint32_t link_cap;   /* [slots][link_cap], power of two */
   DelayEnt *delay_ring; uint32_t delay_cap;/* [slots][delay_cap], power of two */
   uint32_t *slot_counts;                   /* [slots][n_leaves] when counting uses */
@@ -270,12 +274,12 @@ __device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int
 /* ------------------------------------------------------------- the sim ---- */
 template <bool COUNT>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
-                        double *inc_buf, double *hot_send, /* shared memory, element i at [i * blockDim.x] */
+                        double *inc_buf, double *hot_send, uint32_t HS, /* per-tick arrays, element i at [i * HS] */
                         double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
                         double *nsw,                        /* [n_max] SwitchedSender::next_switch_tick, HBM */
+                        SendState *sendst,                  /* [n_max] mirror of the send fields of `cold` */
                         SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
 {
-  const uint32_t HS = blockDim.x; /* stride of the shared-memory hot arrays */
   const uint32_t cand = sim / A.n_cfgs, cfg_i = sim - cand * A.n_cfgs;
   const RemyNetConfig cfg = A.cfgs[cfg_i];
   RemySimResult res;
@@ -432,6 +436,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           } while (nx <= t);
           nsw[s] = nx;
           cold[s] = c;
+          { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
           share[s] = shr;
           const uint32_t bit = 1u << s;
           if (sending) {
@@ -515,6 +520,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         c.leaf = leaf;
         cold[s] = c;
         ak_s = s; ak_seq = c.packets_sent; ak_lim = c.largest_ack + 1 + c.window; ak_isend = c.intersend;
+        { SendState ss; ss.packets_sent = ak_seq; ss.lim = ak_lim; ss.intersend = ak_isend; sendst[s] = ss; }
         const uint32_t bit = 1u << s;
         if (on_mask & bit) {
           const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
@@ -559,8 +565,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           SenderCold *c = &cold[s];
           uint32_t seq; int32_t lim; double isend;
           if (s == ak_s) { seq = ak_seq; lim = ak_lim; isend = ak_isend; ak_seq = seq + 1; }
-          else { seq = c->packets_sent; lim = c->largest_ack + 1 + c->window; isend = c->intersend; }
+          else { const SendState ss = sendst[s]; seq = ss.packets_sent; lim = ss.lim; isend = ss.intersend; }
           c->packets_sent = seq + 1;
+          sendst[s].packets_sent = seq + 1;
           c->last_send_time = t;
           /* Link::accept (link.hh:26-34) */
           if (!pending) {
@@ -579,7 +586,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         if (err) break;
       }
       next_send = ns;
-      if (ns_sender != 0xFFFFFFFFu) prefetch_line(&cold[ns_sender].intersend); /* the sector its send will read */
+      if (ns_sender != 0xFFFFFFFFu) prefetch_line(&sendst[ns_sender]); /* what its transmission will read */
     }
 
     /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) ---- */
@@ -695,12 +702,20 @@ __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs
 {
   extern __shared__ __align__(16) unsigned char smem[];
   /* layout: [inc_buf: INC_BUF*B doubles][hot_send: n_max*B doubles][tree, if staged] */
+#if REMY_HOT_LOCAL
+  /* variant: per-tick arrays in (L1-cached, write-back) local memory instead of shared memory */
+  double hot_local[INC_BUF + REMY_MAX_SENDERS];
+  double *inc_buf = hot_local, *hot_send = hot_local + INC_BUF;
+  const uint32_t HS = 1;
+#else
   double *inc_buf = reinterpret_cast<double *>(smem) + threadIdx.x;
   double *hot_send = inc_buf + (size_t)INC_BUF * blockDim.x;
+  const uint32_t HS = blockDim.x;
+#endif
   TreeView T;
   T.axes_mask = A.axes_mask;
   if (A.tree_in_smem) {
-    unsigned char *p = smem + (size_t)(INC_BUF + A.n_max) * blockDim.x * sizeof(double);
+    unsigned char *p = smem + (REMY_HOT_LOCAL ? 0 : (size_t)(INC_BUF + A.n_max) * blockDim.x * sizeof(double));
     Bounds *sb = reinterpret_cast<Bounds *>(p);
     DevLeaf *sl = reinterpret_cast<DevLeaf *>(sb + (size_t)A.n_nodes * NAX);
     DevNodeMeta *sm = reinterpret_cast<DevNodeMeta *>(sl + A.n_leaves);
@@ -720,13 +735,14 @@ __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs
   SenderCold *cold = A.cold + slot * A.n_max;
   double *share = A.share + slot * A.n_max;
   double *nsw = A.nsw + slot * A.n_max;
+  SendState *sendst = A.sendst + slot * A.n_max;
   LinkEnt *lring = A.link_ring + slot * A.link_cap;
   DelayEnt *dring = A.delay_ring + slot * A.delay_cap;
   uint32_t *cnt = COUNT ? A.slot_counts + slot * A.n_leaves : nullptr;
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT>(A, T, A.order[w], inc_buf, hot_send, share, nsw, cold, lring, dring, cnt);
+    run_sim<COUNT>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
   }
 }
 

@@ -81,3 +81,30 @@ def load_golden_tree(name):
         return abi.default_tree()
     z = np.load(os.path.join(abi.REPO_ROOT, "tests", "golden", "trees", name + ".npz"))
     return abi.FlatTree(z["nodes"], z["leaves"])
+
+
+def random_sweep(n, seed=2026, ticks=1e5):
+    """BASELINE config 5: randomized NetConfigs for a policy-robustness sweep —
+    link ~ U[0.5, 10] ppt, delay ~ U[25, 200] ms, nsrc ~ U{1..32}, buffer in {10, 0.1 BDP, 1 BDP,
+    infinite} equiprobable, loss in {0, 0.01, 0.05} w.p. {.6, .3, .1}, on = off = 5000 ms.
+    (The survey names std::mt19937_64(2026) as the generator; any fixed generator will do for a
+    synthetic sweep — numpy's PCG64 with the same seed is used here and recorded with the results.)"""
+    rng = np.random.default_rng(seed)
+    link = rng.uniform(0.5, 10.0, n)
+    delay = rng.uniform(25.0, 200.0, n)
+    nsrc = rng.integers(1, 33, n)
+    bdp = link * delay
+    kind = rng.integers(0, 4, n)
+    buf = np.where(kind == 0, 10.0, np.where(kind == 1, np.maximum(1.0, np.floor(0.1 * bdp)),
+                                             np.where(kind == 2, np.maximum(1.0, np.floor(bdp)), float(abi.BUFFER_INFINITE))))
+    loss = rng.choice([0.0, 0.01, 0.05], size=n, p=[0.6, 0.3, 0.1])
+    out = np.zeros(n, dtype=abi.net_config_dtype)
+    out["mean_on_duration"] = 5000.0
+    out["mean_off_duration"] = 5000.0
+    out["link_ppt"] = link
+    out["delay"] = delay
+    out["stochastic_loss_rate"] = loss
+    out["simulation_ticks"] = ticks
+    out["num_senders"] = nsrc
+    out["buffer_size"] = buf.astype(np.uint32)
+    return out

@@ -27,6 +27,7 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
   if (link_cap_override) plan.link_cap = link_cap_override;
   const uint32_t n_sims = n_cands * n_cfgs;
   std::vector<SenderCold> cold(plan.n_max);
+  std::vector<SendState> sendst(plan.n_max);
   std::vector<DelayEnt> dring(plan.delay_cap);
   std::vector<uint32_t> cnt(tree->n_leaves);
   std::vector<double> hot(INC_BUF + plan.n_max), share(plan.n_max), nsw(plan.n_max);
@@ -46,8 +47,8 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
     TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
     std::vector<uint32_t> redo;
     for (uint32_t sim : todo) {
-      if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, share.data(), nsw.data(), cold.data(), lring.data(), dring.data(), cnt.data());
-      else run_sim<false>(A, T, sim, hot.data(), hot.data() + INC_BUF, share.data(), nsw.data(), cold.data(), lring.data(), dring.data(), nullptr);
+      if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+      else run_sim<false>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
       if (out_sims[sim].error & REMY_ERR_LINK_OVERFLOW) redo.push_back(sim);
     }
     todo.swap(redo);

@@ -170,6 +170,30 @@ def test_gpu_full_size_properties(device, oracle):
     assert (np.abs(sims[pick]["utility"] - want[0]["utility"]) <= UTILITY_RTOL * np.abs(want[0]["utility"])).all()
 
 
+def test_gpu_random_sweep_sample(device, oracle):
+    """BASELINE config 5 shape at reduced size (16 384 randomized NetConfigs x 2 candidates instead
+    of 1 M): the whole batch runs on the GPU, a 1 % sample is checked bit-exactly against the oracle,
+    and the whole batch through conservation (no packet is created or lost unaccounted)."""
+    tree = workloads.load_golden_tree("RemyCC-2013-delta0.1")
+    cfgs = workloads.random_sweep(16384, seed=2026, ticks=1e4)
+    seeds = workloads.seeds_for(5, len(cfgs))
+    cands = np.zeros(2, dtype=abi.leaf_override_dtype)
+    cands[0] = (0, 0, 0, abi.NO_OVERRIDE)
+    cands[1] = (0.8, 0.5, 2, 3)
+    sims, snd, _ = device.score(tree, cfgs, seeds, cands=cands)
+    assert (sims["error"] == 0).all()
+    # sent = received + still queued + in flight + dropped (buffer drops and stochastic losses)
+    dropped = sims["packets_sent"].astype(np.int64) - sims["packets_received"] - sims["link_queued"] - sims["delay_inflight"]
+    assert (dropped >= 0).all()
+    k = np.arange(len(sims)) % len(cfgs)
+    lossless = (cfgs["stochastic_loss_rate"][k] == 0) & (cfgs["buffer_size"][k] == abi.BUFFER_INFINITE)
+    assert (dropped[lossless] == 0).all() and (dropped[~lossless] > 0).any()
+    pick = np.arange(11, len(cfgs), 100)
+    want = oracle.score(tree, cfgs[pick], seeds[pick], cands=cands, threads=16)
+    rows = np.concatenate([pick, pick + len(cfgs)])
+    assert_same_results((sims[rows], snd[rows], None), want, exact_utility=False, what="sweep sample")
+
+
 def test_gpu_staged_api_matches_one_shot(device):
     tree = workloads.load_golden_tree("RemyCC-2013-delta1")
     cfgs = workloads.default_config_range(ticks=5e3)[::7]
