@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -184,6 +185,9 @@ int pass_geometry(RemyBatch *b, uint32_t n_max, size_t &smem, bool &tree_in_smem
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_fn(b), SIM_BLOCK, smem));
   if (per_sm < 1) return fail(REMY_ECUDA, "kernel does not fit on an SM");
+  /* tuning knob: fewer resident blocks shrink the working set (more of it stays in L2) at the
+   * price of fewer warps to hide latency with */
+  if (const char *cap = getenv("REMY_B200_MAX_BLOCKS_PER_SM")) { const int c = atoi(cap); if (c >= 1 && c < per_sm) per_sm = c; }
   resident_blocks = (uint32_t)per_sm * (uint32_t)g_sms;
   return 0;
 }
@@ -322,6 +326,8 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   /* keep the working memory within a budget: shrink the first-try link ring if needed
    * (overflowing simulations are re-run with larger rings) */
   uint32_t link_cap = plan.link_cap;
+  /* tuning knob: first-try ring size for buffers larger than it (overflowing simulations are re-run) */
+  if (const char *lc = getenv("REMY_B200_LINK_CAP")) { const long c = atol(lc); if (c >= 16 && (uint32_t)c < link_cap) link_cap = next_pow2((uint64_t)c); }
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
   const size_t budget = std::min<size_t>(free_b / 2, (size_t)64 << 30);
