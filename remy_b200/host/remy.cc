@@ -385,10 +385,16 @@ static uint32_t lcg(uint32_t x) { return (uint32_t)(((uint64_t)x * 16807u) % 214
 
 std::vector<uint32_t> Evaluator<WhiskerTree>::seeds(unsigned int prng_seed, size_t n)
 {
+  /* config 0 runs on PRNG(prng_seed) itself — exactly what the reference does (src/evaluator.cc:84),
+   * so a single-config score() is bit-identical to the reference's; config k > 0 gets the k-th
+   * output of that engine instead of wherever config k-1 happened to leave it */
+  std::vector<uint32_t> s(n);
   uint32_t x = prng_seed % 2147483647u;
   if (x == 0) x = 1;
-  std::vector<uint32_t> s(n);
-  for (size_t i = 0; i < n; i++) { x = lcg(x); s[i] = x; }
+  for (size_t i = 0; i < n; i++) {
+    if (i == 0) { s[0] = prng_seed; continue; }
+    x = lcg(x); s[i] = x;
+  }
   return s;
 }
 

@@ -201,7 +201,8 @@ public:
   /* The data-parallel replacement for ActionImprover::evaluate_replacements
    * (src/breeder.cc:53-77): scores[c] = score of `tree` with replacements[c] applied. */
   std::vector<double> score_candidates(const WhiskerTree &tree, const std::vector<Whisker> &replacements, double carefulness = 1) const;
-  /* per-config seeds of a score() call: the first n outputs of minstd_rand0(prng_seed) */
+  /* per-config seeds of a score() call: prng_seed itself for config 0 (as in the reference), then the
+   * successive outputs of minstd_rand0(prng_seed) */
   static std::vector<uint32_t> seeds(unsigned int prng_seed, size_t n);
 };
 

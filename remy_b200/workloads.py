@@ -33,12 +33,17 @@ def default_config_range(ticks=1e6, link=(1.0, 2.0, 0.25), rtt=(100.0, 200.0, 25
 
 
 def seeds_for(evaluator_seed, n):
-    """Per-config seeds: the first n outputs of minstd_rand0(evaluator_seed) — the batched
-    evaluator's replacement for the single chained PRNG of src/evaluator.cc:84."""
+    """Per-config seeds of one Evaluator: config 0 runs on PRNG(evaluator_seed) itself, exactly
+    like the reference (src/evaluator.cc:84), so a single-config score is bit-identical to the
+    reference's; config k > 0 gets the k-th output of minstd_rand0(evaluator_seed) — the batched
+    evaluator's replacement for the one PRNG the reference chains through all configs."""
     m = 2147483647
     x = evaluator_seed % m or 1
     out = np.empty(n, dtype=np.uint32)
     for i in range(n):
+        if i == 0:
+            out[0] = evaluator_seed & 0xFFFFFFFF
+            continue
         x = (x * 16807) % m
         out[i] = x
     return out

@@ -1,0 +1,51 @@
+"""sender-runner CLI (reference src/sender-runner.cc) on the GPU: stdout format and numbers.
+
+Mirrors the reference's own CLI regression test tests/verify-2014-10.test (via
+tests/verify-2014-100x-results.pm): RemyCC-2014-100x, 2 senders, link 9.93 Mbit/s, RTT 150 ms,
+on = off = 1000 ms -> every sender's throughput within 5 % of 6.0 Mbit/s and delay within 5 % of
+165 ms — here with a fixed seed (an extension; the reference seeds from time ^ pid), and
+additionally pinned digit-for-digit against the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+from remy_b200 import abi, hostlib, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sender_runner_verify_2014_10(built, device, oracle, tmp_path):
+    built.build_host()
+    host = hostlib.HostLib()
+    flat = workloads.load_golden_tree("RemyCC-2014-100x")
+    dna_path = tmp_path / "RemyCC-2014-100x.dna"
+    dna_path.write_bytes(host.tree_from_flat(flat).serialize())
+    link_mbps = 9.93
+    exe = os.path.join(ROOT, "remy_b200", "host", "sender-runner")
+    out = subprocess.run([exe, f"if={dna_path}", "nsrc=2", f"link={link_mbps / 10}", "rtt=150", "on=1000", "off=1000",
+                          "seed=7", "ticks=100000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    senders = re.findall(r"sender: \[tp=([0-9.eE+-]+), del=([0-9.eE+-]+)\]", out.stdout)
+    assert len(senders) == 2
+    for tp, dl in senders:   # tests/verify-2014-100x-results.pm:20-37
+        raw_tput = float(tp) * 0.75 * link_mbps
+        raw_delay = float(dl) * 150
+        assert abs(raw_tput - 6.0) <= 0.05 * 6.0 and abs(raw_delay - 165) <= 0.05 * 165, (raw_tput, raw_delay)
+    # digit-for-digit against the oracle: carefulness 10 x 100000 ticks, seed_0 = seed
+    cfg = abi.make_configs([dict(link_ppt=link_mbps / 10, delay=150, num_senders=2, mean_on_duration=1000,
+                                 mean_off_duration=1000, simulation_ticks=1e6)])
+    sims, snd, _ = oracle.score(flat, cfg, np.array([7], dtype=np.uint32))
+    want = []
+    for s in range(2):
+        r = snd[0][s]
+        want.append(("%f" % (r["packets_received"] / r["tick_share_sending"] / cfg[0]["link_ppt"]),
+                     "%f" % (r["total_delay"] / r["packets_received"] / 150.0)))
+    assert senders == want
+    assert ("score = %f" % sims[0]["utility"]) in out.stdout
+    assert "config: mean_on=1000.000000, mean_off=1000.000000, nsrc=2.000000, link_ppt=0.993000, delay=150.000000" in out.stdout
+    assert re.search(r"^normalized_score = -?[0-9.]+$", out.stdout, re.M) and "Rules: [{(lo=< sewma=" in out.stdout
+    assert out.stdout.startswith("Prior assumptions:\nlink_packets_per_ms {\n  low: 0.316227766016838")

@@ -71,3 +71,27 @@ def test_score_candidates_matches_oracle(host, oracle):
             w += float(u)
         assert abs(got[c] - w) <= 1e-9 * abs(w), c
     assert got[0] == tree.score(raw, seed)[0]                  # candidate 0 is the unchanged whisker
+
+
+def test_single_config_equals_reference(host, reference):
+    """sender-runner's shape: a ConfigRange with one point.  The reference's Evaluator runs its
+    only Network on PRNG(seed); so does ours (seed_0 = seed), so score and per-sender
+    (throughput, delay) must equal the reference's PUBLIC Evaluator<WhiskerTree>::score — called
+    here through oracle/_ref, i.e. the reference's own unmodified evaluator.cc."""
+    inf = float(abi.BUFFER_INFINITE)
+    for tree_name, link, rtt, n, on, off, buf in (("RemyCC-2014-100x", 0.993, 150, 2, 1000, 1000, inf),
+                                                  ("RemyCC-2013-delta1", 1.5, 150, 8, 10000, 10000, inf),
+                                                  ("default", 2.0, 50, 2, 5000, 500, 10.0)):
+        flat = workloads.load_golden_tree(tree_name)
+        tree = host.tree_from_flat(flat)
+        raw = hostlib.encode_config_range(link=(link, link, 0), rtt=(rtt, rtt, 0), nsrc=(n, n, 0), buf=(buf, buf, 0),
+                                          off=(off, off, 0), on=(on, on, 0), ticks=200000)
+        cfgs, _ = host.expand(raw)
+        assert len(cfgs) == 1
+        for seed in (1, 4242, 2147483648 + 17):
+            score, counts, td = tree.score(raw, seed)
+            sims, snd, ref_counts = reference.score(flat, cfgs, np.array([seed], dtype=np.uint32), want_use_counts=True, mode=1)
+            assert abs(score - sims[0]["utility"]) <= 1e-9 * abs(score)
+            for s in range(n):   # mode 1 returns (normalised throughput, average delay) per sender
+                assert td[s][0] == snd[0][s]["tick_share_sending"] and td[s][1] == snd[0][s]["total_delay"]
+            assert (counts == ref_counts[0]).all()
