@@ -40,6 +40,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def build_improve_step(args, dev):
+    """BASELINE configs[2]: one ActionImprover::evaluate_replacements fan-out (src/breeder.cc:53-77) as ONE
+    batch: score the tree once with use counts, take the most used whisker whose action the optimizer may
+    vary (WhiskerTree::most_used, src/whiskertree.cc:84-109), generate its candidates with the C++ mirror of
+    Whisker::next_generation, and score candidates x the default ConfigRange at carefulness 0.1."""
+    from remy_b200 import hostlib
+    import __graft_entry__ as g
+    g.build_host()
+    tree = workloads.load_golden_tree(args.tree)
+    cfgs = workloads.default_config_range(ticks=args.ticks)
+    seeds = workloads.seeds_for(2026, len(cfgs))
+    _, _, counts = dev.score(tree, cfgs, seeds, want_senders=False, want_use_counts=True)
+    host = hostlib.HostLib()
+    ht = host.tree_from_flat(tree)
+    order = np.argsort(-counts[0].astype(np.int64))
+    for leaf in order:
+        l = tree.leaves[leaf]
+        if 0 <= l["window_increment"] <= 256 and 0 <= l["window_multiple"] <= 1 and 0.25 <= l["intersend"] <= 3:
+            cands = ht.next_generation(int(leaf))
+            return tree, cfgs, seeds, cands, int(leaf)
+    raise SystemExit("no whisker with an optimizable action")
+
+
 def build_workload(args, rank):
     tree = workloads.load_golden_tree(args.tree)
     base = workloads.default_config_range(ticks=args.ticks)
@@ -147,6 +170,9 @@ def main():
     ap.add_argument("--replicas", type=int, default=192, help="evaluator seeds per GPU (x 800 NetConfigs)")
     ap.add_argument("--tree", default="RemyCC-2014-100x")
     ap.add_argument("--cpu-stride", type=int, default=4)
+    ap.add_argument("--workload", default="evaluator-pass", choices=["evaluator-pass", "improve-step"],
+                    help="evaluator-pass: BASELINE configs[1] (the bench line of record); improve-step: BASELINE configs[2], "
+                         "every Whisker::next_generation candidate of the most used whisker x the 800 NetConfigs in one batch")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,8 +231,16 @@ def main():
         flush_buf.fill_(1)
         torch.cuda.synchronize()
 
+    cands = None
+    if args.workload == "improve-step":
+        tree, cfgs, seeds, cands, leaf = build_improve_step(args, dev)
+        config["workload"] = (f"BASELINE configs[2]: one RatBreeder improve fan-out — {len(cands)} Whisker::next_generation candidates of "
+                              f"leaf {leaf} of {args.tree} x 800 NetConfigs (default ConfigRange), {args.ticks:g} ticks, one batch per GPU")
+        config["sims_per_gpu"] = int(len(cands) * len(cfgs))
+        args.replicas = 1
+
     # value: staged API, inputs resident in HBM
-    batch = dev.create_batch(tree, cfgs, seeds, want_senders=False, want_use_counts=False)
+    batch = dev.create_batch(tree, cfgs, seeds, cands=cands, want_senders=False, want_use_counts=False)
     for _ in range(args.warmup):
         batch.run(timed=True)
         flush_l2()
@@ -230,11 +264,11 @@ def main():
     p_cfgs, k1 = pinned_like(cfgs)
     p_seeds, k2 = pinned_like(seeds)
     for _ in range(1):
-        dev.score(tree, p_cfgs, p_seeds, want_senders=False)
+        dev.score(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e_sims, _, _ = dev.score(tree, p_cfgs, p_seeds, want_senders=False)
+        e_sims, _, _ = dev.score(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
         score = float(e_sims["utility"].sum())  # the step's result, read on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -288,6 +322,8 @@ def main():
                 "cpu_baseline": cpu,
                 "event_ticks_per_sec": ticks_all * args.steps / secs, "sims_per_sec": sims_all * args.steps / secs,
                 "evals_per_sec": sims_all / 800.0 * args.steps / secs, "score_sum": score_all}
+        if cands is not None:
+            line["candidates"] = int(len(cands))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

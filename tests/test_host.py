@@ -114,3 +114,19 @@ def test_reference_cfg_files(host):
     raw = open(os.path.join(REF, "config", "2_2_really_small_buffer_0.cfg"), "rb").read()
     g = host.expand(raw)[0][0]
     assert (g["link_ppt"], g["delay"], g["num_senders"], g["buffer_size"], g["mean_off_duration"], g["simulation_ticks"]) == (2.0, 50.0, 2, 10, 500.0, 600000.0)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference not present")
+def test_sender_runner_prints_tree_like_protobuf(host):
+    """print_tree (src/sender-runner.cc:15-25) shows DebugString() of the tree's config and
+    optimizer sub-messages before scoring; without a GPU the run then fails loudly."""
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "remy_b200", "host", "sender-runner")
+    out = subprocess.run([exe, "if=" + os.path.join(REF, "tests", "RemyCC-2014-100x.dna"), "nsrc=2", "link=0.993", "ticks=10"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.stdout.startswith("Prior assumptions:\nlink_packets_per_ms {\n  low: 0.316227766016838\n  high: 31.6227766016838\n}\nrtt {\n  low: 150\n  high: 150\n}\n")
+    assert "Remy optimization settings:\nwindow_increment {\n  min_value: 0\n  max_value: 256\n  min_change: 1\n  max_change: 32\n  multiplier: 4\n  default_value: 1\n}\n" in out.stdout
+    assert "Setting num_senders to 2" in out.stderr
+    if not torch.cuda.is_available():
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
