@@ -112,7 +112,7 @@ namespace {
 
 size_t smem_bytes(const RemyBatch *b, uint32_t n_max, bool with_tree)
 {
-  return (REMY_HOT_LOCAL ? 0 : (size_t)(INC_BUF + n_max) * SIM_BLOCK * sizeof(double)) + (with_tree ? b->tree_bytes : 0);
+  return (size_t)(INC_BUF + n_max) * SIM_BLOCK * sizeof(double) + (with_tree ? b->tree_bytes : 0);
 }
 
 const void *kernel_fn(const RemyBatch *b)

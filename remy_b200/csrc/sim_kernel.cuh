@@ -56,12 +56,6 @@
 namespace remy {
 
 constexpr uint32_t LCG_M = 2147483647u;
-#ifndef REMY_HOT_LOCAL
-#define REMY_HOT_LOCAL 0
-#endif
-#ifndef REMY_ACK_GATE
-#define REMY_ACK_GATE 0 /* max iterations a lane with mail waits for its warp; 0 disables the gate (measured: -15% on B200) */
-#endif
 constexpr uint32_t INC_BUF = 8; /* buffered sending-time increments per simulation (shared memory) */
 
 struct KernelArgs {
@@ -92,14 +86,12 @@ struct KernelArgs {
   uint32_t *out_use_counts;                /* [n_cands][n_leaves], optional */
 };
 
-/* Non-binding request to bring the line holding p towards the SM (HBM/L2 latency of the
- * next ack's state is the kernel's main stall; the address is known ticks in advance). */
+/* Non-binding request to bring the line holding p towards the SM: used where an address is
+ * known ticks before its data is needed (next ring line, the next sender to transmit). */
 __device__ __forceinline__ void prefetch_line(const void *p)
 {
-#if defined(REMY_HOST_EMU) || (defined(REMY_PREFETCH) && REMY_PREFETCH == 0)
+#ifdef REMY_HOST_EMU
   (void)p;
-#elif defined(REMY_PREFETCH) && REMY_PREFETCH == 2
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #else
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #endif
@@ -365,26 +357,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     ninc = 0;
   };
 
-  uint32_t waited = 0;
   while (t < duration) {
-#if REMY_ACK_GATE
-    /* Warp-level phase alignment.  A tick that starts with mail (ack -> Memory update -> tree
-     * lookup -> usually a transmission) is several times heavier than a plain tick, and in any
-     * given loop iteration only a fraction of a warp's lanes is at that point, so the heavy code
-     * would run with few active lanes every iteration.  Lanes with mail therefore idle until at
-     * least half of the warp's running lanes have mail too (or they have waited two iterations):
-     * the heavy path then runs once, nearly converged.  Neighbouring lanes run the same config
-     * (the work list is sorted by config), hence the same link/delay period, and stay aligned.
-     * Idling does not touch simulation state, so results are unchanged. */
-    {
-      const bool mail = dcons != ddeliv;
-      const unsigned act = __activemask();
-      const unsigned mm = __ballot_sync(act, mail);
-      const unsigned late = __ballot_sync(act, mail && waited >= REMY_ACK_GATE);
-      if (mail && !late && 2 * __popc(mm) < __popc(act)) { waited++; continue; }
-      waited = 0;
-    }
-#endif
     /* ---- next event (network.cc:75-78) ---- */
     double tn = fmax(t, fmin(min_switch, next_send)); /* SenderGang::next_event_time */
     if (pending) tn = fmin(tn, pend_release);           /* Link::next_event_time */
@@ -702,20 +675,13 @@ __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs
 {
   extern __shared__ __align__(16) unsigned char smem[];
   /* layout: [inc_buf: INC_BUF*B doubles][hot_send: n_max*B doubles][tree, if staged] */
-#if REMY_HOT_LOCAL
-  /* variant: per-tick arrays in (L1-cached, write-back) local memory instead of shared memory */
-  double hot_local[INC_BUF + REMY_MAX_SENDERS];
-  double *inc_buf = hot_local, *hot_send = hot_local + INC_BUF;
-  const uint32_t HS = 1;
-#else
   double *inc_buf = reinterpret_cast<double *>(smem) + threadIdx.x;
   double *hot_send = inc_buf + (size_t)INC_BUF * blockDim.x;
   const uint32_t HS = blockDim.x;
-#endif
   TreeView T;
   T.axes_mask = A.axes_mask;
   if (A.tree_in_smem) {
-    unsigned char *p = smem + (REMY_HOT_LOCAL ? 0 : (size_t)(INC_BUF + A.n_max) * blockDim.x * sizeof(double));
+    unsigned char *p = smem + (size_t)(INC_BUF + A.n_max) * blockDim.x * sizeof(double);
     Bounds *sb = reinterpret_cast<Bounds *>(p);
     DevLeaf *sl = reinterpret_cast<DevLeaf *>(sb + (size_t)A.n_nodes * NAX);
     DevNodeMeta *sm = reinterpret_cast<DevNodeMeta *>(sl + A.n_leaves);

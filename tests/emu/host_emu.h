@@ -42,8 +42,6 @@ static inline int32_t __double2int_rz(double v)
   if (v <= -2147483648.0) return (int32_t)0x80000000;
   return (int32_t)v;
 }
-static inline unsigned __activemask() { return 1u; }
-static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 using std::max;
 using std::min;
