@@ -4,6 +4,7 @@
  * include/remy_b200.h); exceptions are turned into return codes + remy_host_last_error().
  */
 #include "remy.hh"
+#include "breeder.hh"
 
 #include <cstring>
 #include <stdexcept>
@@ -124,6 +125,44 @@ long remy_host_score_next_generation(void *h, const void *range_bytes, size_t ra
     const std::vector<double> s = e.score_candidates(t, gen, carefulness);
     for (size_t i = 0; i < s.size() && i < cap; i++) scores[i] = s[i];
     return (long)s.size();)
+}
+
+/* WhiskerImprover::improve on leaf `leaf_index` of the tree, repeated until the score stops rising
+ * (the inner loop of RatBreeder::improve, src/ratbreeder.cc:39-49).  Needs a GPU.  Returns the number of
+ * improve() calls; out = {score_to_beat, chosen increment, multiple, intersend, candidates scored, batches}. */
+long remy_host_improve_whisker(void *h, const void *range_bytes, size_t range_size, unsigned int prng_seed, uint32_t leaf_index, double *out)
+{
+  GUARD(
+    WhiskerTree &t = *(WhiskerTree *)h;
+    std::vector<const Whisker *> lv; t.leaves(lv);
+    if (leaf_index >= lv.size()) throw std::runtime_error("leaf index out of range");
+    Evaluator<WhiskerTree> e(ConfigRange::parse(range_bytes, range_size), prng_seed);
+    auto outcome = e.score(t);
+    WhiskerImprover improver(e, t, WhiskerImproverOptions(), outcome.score);
+    Whisker w = *lv[leaf_index];
+    double score_to_beat = outcome.score;
+    long calls = 0;
+    for (;;) {
+      const double ns = improver.improve(w); calls++;
+      if (ns == score_to_beat) break;
+      score_to_beat = ns;
+    }
+    out[0] = score_to_beat; out[1] = w.window_increment(); out[2] = w.window_multiple(); out[3] = w.intersend();
+    out[4] = (double)improver.candidates_scored; out[5] = (double)improver.batches;
+    return calls;)
+}
+
+/* RatBreeder::improve (without apply_best_split); the tree behind `h` is updated in place */
+int remy_host_ratbreeder_improve(void *h, const void *range_bytes, size_t range_size, unsigned int seed, double *score, double *stats)
+{
+  GUARD(
+    WhiskerTree &t = *(WhiskerTree *)h;
+    BreederOptions o; o.config_range = ConfigRange::parse(range_bytes, range_size);
+    RatBreeder b(o, WhiskerImproverOptions(), seed);
+    const auto outcome = b.improve(t);
+    *score = outcome.score;
+    if (stats) { stats[0] = (double)b.candidates_scored; stats[1] = (double)b.batches; }
+    return 0;)
 }
 
 } /* extern "C" */

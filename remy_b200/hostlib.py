@@ -31,6 +31,9 @@ class HostLib:
         L.remy_host_config_range_expand.argtypes = [C.c_char_p, C.c_size_t, C.c_double, _V, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_long)]
         L.remy_host_evaluator_score.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.POINTER(C.c_double), _V, C.c_uint32,
                                                 _V, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.remy_host_improve_whisker.restype = C.c_long
+        L.remy_host_improve_whisker.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint32, _V]
+        L.remy_host_ratbreeder_improve.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_double), _V]
         L.remy_host_score_next_generation.restype = C.c_long
         L.remy_host_score_next_generation.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.c_uint32, _V, C.c_uint32]
 
@@ -110,6 +113,20 @@ class HostTree:
                                                       counts.ctypes.data, len(counts), td.ctypes.data, len(td), C.byref(n_td))
         self.host._check(rc == 0)
         return score.value, counts, td[:n_td.value].reshape(-1, 2).copy()
+
+    def improve_whisker(self, range_bytes, prng_seed, leaf):
+        """WhiskerImprover::improve repeated until the score stops rising -> (calls, score, (incr, mult, intersend), candidates, batches)."""
+        out = np.zeros(6, dtype=np.float64)
+        n = self.host.lib.remy_host_improve_whisker(self.h, range_bytes, len(range_bytes), prng_seed, leaf, out.ctypes.data)
+        self.host._check(n >= 0)
+        return int(n), float(out[0]), (int(out[1]), float(out[2]), float(out[3])), int(out[4]), int(out[5])
+
+    def ratbreeder_improve(self, range_bytes, seed):
+        score = C.c_double(0)
+        stats = np.zeros(2, dtype=np.float64)
+        rc = self.host.lib.remy_host_ratbreeder_improve(self.h, range_bytes, len(range_bytes), seed, C.byref(score), stats.ctypes.data)
+        self.host._check(rc == 0)
+        return score.value, int(stats[0]), int(stats[1])
 
     def score_next_generation(self, range_bytes, prng_seed, leaf, carefulness=1.0):
         out = np.zeros(512, dtype=np.float64)

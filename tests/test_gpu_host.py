@@ -95,3 +95,89 @@ def test_single_config_equals_reference(host, reference):
             for s in range(n):   # mode 1 returns (normalised throughput, average delay) per sender
                 assert td[s][0] == snd[0][s]["tick_share_sending"] and td[s][1] == snd[0][s]["total_delay"]
             assert (counts == ref_counts[0]).all()
+
+
+def _alternatives(value, lo, hi, min_change, max_change, mult, unsigned):
+    """OptimizationSetting::alternatives (src/action.hh:62-91)."""
+    out = [value]
+    c = min_change
+    while c <= max_change:
+        up, down = value + c, value - c
+        if unsigned and down < 0:
+            down = down + 2 ** 32                                  # unsigned wrap: never eligible
+        if lo <= up <= hi:
+            out.append(up)
+        if lo <= down <= hi:
+            out.append(down)
+        c *= mult
+    return out
+
+
+def _next_generation(w):
+    """Whisker::next_generation + round (src/whisker.cc:46-95) for action w = (incr, mult, intersend)."""
+    rnd = lambda v: (1.0 / 10000.0) * int(10000 * v)
+    return [(i, rnd(m), rnd(s)) for i in _alternatives(w[0], 0, 256, 1, 32, 4, True)
+            for m in _alternatives(w[1], 0.0, 1.0, 0.01, 0.5, 4, False)
+            for s in _alternatives(w[2], 0.25, 3.0, 0.05, 1.0, 4, False)]
+
+
+def test_whisker_improver_matches_oracle_driven_restatement(host, oracle):
+    """ActionImprover::improve / early_bail_out / evaluate_replacements (src/breeder.cc:53-150) on the GPU
+    path against a line-by-line Python restatement of the same control flow that scores with the oracle:
+    same number of improve() rounds, same chosen action, same final score."""
+    import math
+    flat = abi.default_tree()
+    tree = host.tree_default()
+    inf = float(abi.BUFFER_INFINITE)
+    raw = hostlib.encode_config_range(link=(1, 2, 1), rtt=(100, 200, 100), nsrc=(1, 9, 4), buf=(inf, inf, 0),
+                                      off=(2000, 2000, 0), on=(2000, 2000, 0), ticks=20000)
+    seed = 99
+    calls, score, action, n_scored, batches = tree.improve_whisker(raw, seed, 0)
+
+    cfg_full, _ = host.expand(raw)
+    cfg_fast, _ = host.expand(raw, carefulness=0.1)
+    seeds = workloads.seeds_for(seed, len(cfg_full))
+
+    def score_many(cands, cfgs):
+        arr = np.zeros(len(cands), dtype=abi.leaf_override_dtype)
+        for i, (inc, mul, isend) in enumerate(cands):
+            arr[i] = (mul, isend, inc, 0)
+        sims, _, _ = oracle.score(flat, cfgs, seeds, cands=arr, want_senders=False, threads=16)
+        u = sims["utility"].reshape(len(cands), len(cfgs))
+        out = []
+        for c in range(len(cands)):
+            t = 0.0
+            for v in u[c]:
+                t += float(v)
+            out.append(t)
+        return out
+
+    cache = {}
+
+    def evaluate(cands, cfgs):
+        fresh = [c for c in cands if c not in cache]
+        got = dict(zip(fresh, score_many(fresh, cfgs))) if fresh else {}
+        return [(c in got, got[c] if c in got else cache[c]) for c in cands]
+
+    w = (1, 1.0, 3.0)
+    to_beat = score_many([w], cfg_full)[0]
+    py_calls = 0
+    while True:
+        reps = _next_generation(w)
+        raw_scores = [s for _, s in evaluate(reps, cfg_fast)]
+        lower = min(to_beat * 1.05, to_beat * 0.95)
+        ranked = sorted(raw_scores, reverse=True)
+        cutoff = max(lower, ranked[math.ceil(len(ranked) * 0.5) - 1])
+        top = [r for r, s in zip(reps, raw_scores) if s >= cutoff]
+        before = to_beat
+        for r, (new, s) in zip(top, evaluate(top, cfg_full)):
+            if new:
+                cache[r] = s
+            if s > to_beat:
+                to_beat, w = s, r
+        py_calls += 1
+        if to_beat == before:
+            break
+    assert calls == py_calls and action == w, (calls, py_calls, action, w)
+    assert abs(score - to_beat) <= 1e-9 * abs(to_beat)
+    assert batches <= 2 * calls and n_scored >= 80          # two batch calls per improve(), not one thread per candidate
