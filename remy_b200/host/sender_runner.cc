@@ -94,50 +94,54 @@ int main(int argc, char *argv[])
       return 1;
     }
   }
+  /* key=value arguments: the numeric ones are table-driven; each echoes the reference's stderr line */
+  struct NumArg { const char *key; double *dst; const char *echo; };
+  double nsrc_arg = num_senders;
+  const NumArg table[] = {
+    { "nsrc=", &nsrc_arg, "Setting num_senders to %.0f\n" },
+    { "link=", &link_ppt, "Setting link packets per ms to %f\n" },
+    { "rtt=", &delay, "Setting delay to %f ms\n" },
+    { "on=", &mean_on_duration, "Setting mean_on_duration to %f ms\n" },
+    { "off=", &mean_off_duration, "Setting mean_off_duration to %f ms\n" },
+    { "sloss=", &stochastic_loss_rate, "Setting stochastic loss rate to %f\n" },
+  };
   for (int i = 1; i < argc; i++) {
-    string arg(argv[i]);
-    if (arg.substr(0, 3) == "if=") {
-      const string raw = slurp(arg.substr(3));
+    const string arg(argv[i]);
+    const size_t eq = arg.find('=');
+    if (eq == string::npos) continue;
+    const string key = arg.substr(0, eq + 1), val = arg.substr(eq + 1);
+    bool numeric = false;
+    for (const NumArg &a : table) {
+      if (key != a.key) continue;
+      *a.dst = (a.dst == &nsrc_arg) ? (double)atoi(val.c_str()) : atof(val.c_str());
+      fprintf(stderr, a.echo, *a.dst);
+      numeric = true;
+    }
+    if (numeric) continue;
+    if (key == "if=") {
+      const string raw = slurp(val);
       try { whiskers = WhiskerTree::parse(raw.data(), raw.size()); }
-      catch (const exception &e) { fprintf(stderr, "Could not parse %s.\n", arg.substr(3).c_str()); return 1; }
+      catch (const exception &e) { fprintf(stderr, "Could not parse %s.\n", val.c_str()); return 1; }
       print_tree(raw);
-    } else if (arg.substr(0, 3) == "cf=") {
-      const string raw = slurp(arg.substr(3));
+    } else if (key == "cf=") {
+      const string raw = slurp(val);
       const ConfigRange r = ConfigRange::parse(raw.data(), raw.size());
-      link_ppt = r.link_ppt.low; delay = r.rtt.low; num_senders = (unsigned int)r.num_senders.low;
+      link_ppt = r.link_ppt.low; delay = r.rtt.low; nsrc_arg = (unsigned int)r.num_senders.low;
       buffer_size = r.buffer_size.low; mean_off_duration = r.mean_off_duration.low;
       mean_on_duration = r.mean_on_duration.low > 0 ? r.mean_on_duration.low : 5000.0;
       stochastic_loss_rate = r.stochastic_loss_rate.low;
       if (r.simulation_ticks) simulation_ticks = r.simulation_ticks;
-    } else if (arg.substr(0, 5) == "nsrc=") {
-      num_senders = atoi(arg.substr(5).c_str());
-      fprintf(stderr, "Setting num_senders to %d\n", num_senders);
-    } else if (arg.substr(0, 5) == "link=") {
-      link_ppt = atof(arg.substr(5).c_str());
-      fprintf(stderr, "Setting link packets per ms to %f\n", link_ppt);
-    } else if (arg.substr(0, 4) == "rtt=") {
-      delay = atof(arg.substr(4).c_str());
-      fprintf(stderr, "Setting delay to %f ms\n", delay);
-    } else if (arg.substr(0, 3) == "on=") {
-      mean_on_duration = atof(arg.substr(3).c_str());
-      fprintf(stderr, "Setting mean_on_duration to %f ms\n", mean_on_duration);
-    } else if (arg.substr(0, 4) == "off=") {
-      mean_off_duration = atof(arg.substr(4).c_str());
-      fprintf(stderr, "Setting mean_off_duration to %f ms\n", mean_off_duration);
-    } else if (arg.substr(0, 4) == "buf=") {
-      if (arg.substr(4) == "inf") buffer_size = numeric_limits<unsigned int>::max();
-      else buffer_size = atoi(arg.substr(4).c_str());
-    } else if (arg.substr(0, 6) == "sloss=") {
-      stochastic_loss_rate = atof(arg.substr(6).c_str());
-      fprintf(stderr, "Setting stochastic loss rate to %f\n", stochastic_loss_rate);
-    } else if (arg.substr(0, 5) == "seed=") {
-      seed = (unsigned int)strtoul(arg.substr(5).c_str(), nullptr, 10);
-    } else if (arg.substr(0, 6) == "ticks=") {
-      simulation_ticks = (unsigned int)strtoul(arg.substr(6).c_str(), nullptr, 10);
-    } else if (arg.substr(0, 4) == "dev=") {
-      device = atoi(arg.substr(4).c_str());
+    } else if (key == "buf=") {
+      buffer_size = (val == "inf") ? (double)numeric_limits<unsigned int>::max() : (double)atoi(val.c_str());
+    } else if (key == "seed=") {
+      seed = (unsigned int)strtoul(val.c_str(), nullptr, 10);
+    } else if (key == "ticks=") {
+      simulation_ticks = (unsigned int)strtoul(val.c_str(), nullptr, 10);
+    } else if (key == "dev=") {
+      device = atoi(val.c_str());
     }
   }
+  num_senders = (unsigned int)nsrc_arg;
 
   ConfigRange configuration_range;
   configuration_range.link_ppt = Range(link_ppt, link_ppt, 0);
