@@ -127,6 +127,28 @@ long remy_host_score_next_generation(void *h, const void *range_bytes, size_t ra
     return (long)s.size();)
 }
 
+/* Evaluator::DNA(tree): ProblemBuffers.Problem bytes for a (range, seed, tree) — no GPU needed */
+long remy_host_problem_dna(void *h, const void *range_bytes, size_t range_size, unsigned int prng_seed, char *buf, size_t cap)
+{
+  GUARD(
+    Evaluator<WhiskerTree> e(ConfigRange::parse(range_bytes, range_size), prng_seed);
+    return copy_out(e.DNA(*(WhiskerTree *)h), buf, cap);)
+}
+
+/* parse_problem_and_evaluate(Problem bytes) -> AnswerBuffers.Outcome bytes — needs a GPU */
+long remy_host_solve_problem(const void *problem, size_t size, char *buf, size_t cap)
+{
+  GUARD(
+    const auto outcome = Evaluator<WhiskerTree>::parse_problem_and_evaluate(problem, size);
+    return copy_out(outcome.DNA(), buf, cap);)
+}
+
+/* Outcome(AnswerBuffers::Outcome).DNA() round trip — no GPU needed */
+long remy_host_answer_roundtrip(const void *answer, size_t size, char *buf, size_t cap)
+{
+  GUARD(return copy_out(Evaluator<WhiskerTree>::Outcome::parse(answer, size).DNA(), buf, cap);)
+}
+
 /* WhiskerImprover::improve on leaf `leaf_index` of the tree, repeated until the score stops rising
  * (the inner loop of RatBreeder::improve, src/ratbreeder.cc:39-49).  Needs a GPU.  Returns the number of
  * improve() calls; out = {score_to_beat, chosen increment, multiple, intersend, candidates scored, batches}. */

@@ -77,6 +77,34 @@ std::string NetConfig::str() const
            mean_on_duration, mean_off_duration, num_senders, link_ppt, delay, buffer_size, stochastic_loss_rate);
   return tmp;
 }
+std::string NetConfig::DNA() const
+{ /* src/network.hh:57-70: all eight fields are set; num_senders / buffer_size / simulation_ticks are uint32 */
+  pb::Writer w;
+  w.put_double(1, mean_on_duration); w.put_double(2, mean_off_duration); w.put_varint(3, (uint32_t)num_senders);
+  w.put_double(4, link_ppt); w.put_double(5, delay); w.put_varint(6, (uint32_t)buffer_size);
+  w.put_double(7, stochastic_loss_rate); w.put_varint(8, (uint32_t)simulation_ticks);
+  return w.str();
+}
+NetConfig NetConfig::parse(const void *data, size_t size)
+{ /* NetConfig(const RemyBuffers::NetConfig &) (src/network.hh:38-47): absent fields read as 0 */
+  NetConfig c;
+  c.mean_on_duration = c.mean_off_duration = c.num_senders = c.link_ppt = c.delay = c.buffer_size = c.stochastic_loss_rate = c.simulation_ticks = 0;
+  pb::Reader rd(data, size); pb::Field f;
+  while (rd.next(f)) {
+    switch (f.number) {
+      case 1: if (f.wire_type == 1) c.mean_on_duration = pb::Reader::as_double(f); break;
+      case 2: if (f.wire_type == 1) c.mean_off_duration = pb::Reader::as_double(f); break;
+      case 3: if (f.wire_type == 0) c.num_senders = (uint32_t)f.varint; break;
+      case 4: if (f.wire_type == 1) c.link_ppt = pb::Reader::as_double(f); break;
+      case 5: if (f.wire_type == 1) c.delay = pb::Reader::as_double(f); break;
+      case 6: if (f.wire_type == 0) c.buffer_size = (uint32_t)f.varint; break;
+      case 7: if (f.wire_type == 1) c.stochastic_loss_rate = pb::Reader::as_double(f); break;
+      case 8: if (f.wire_type == 0) c.simulation_ticks = (uint32_t)f.varint; break;
+      default: break;
+    }
+  }
+  return c;
+}
 RemyNetConfig NetConfig::pod(double ticks_to_run) const
 {
   RemyNetConfig c;
@@ -472,6 +500,72 @@ Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_w
 Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_actions, bool trace, double carefulness) const
 { /* src/evaluator.cc:196-201 */
   return score(run_actions, _prng_seed, _configs, trace, _tick_count * carefulness);
+}
+
+std::string Evaluator<WhiskerTree>::DNA(const WhiskerTree &whiskers) const
+{ /* src/evaluator.cc:40-66 */
+  pb::Writer settings; settings.put_varint(11, _prng_seed); settings.put_varint(12, _tick_count);
+  pb::Writer w;
+  w.put_message(1, settings.str());
+  for (const auto &x : _configs) w.put_message(2, x.DNA());
+  w.put_message(3, whiskers.DNA());
+  return w.str();
+}
+
+Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::parse_problem_and_evaluate(const void *problem, size_t size)
+{ /* src/evaluator.cc:134-146 */
+  std::vector<NetConfig> configs;
+  WhiskerTree run_whiskers;
+  unsigned int prng_seed = 0, tick_count = 0;
+  bool have_tree = false;
+  pb::Reader rd(problem, size); pb::Field f;
+  while (rd.next(f)) {
+    if (f.wire_type != 2) continue;
+    if (f.number == 1) {
+      pb::Reader sr(f.data, f.size); pb::Field g;
+      while (sr.next(g)) { if (g.number == 11 && g.wire_type == 0) prng_seed = (unsigned int)g.varint; else if (g.number == 12 && g.wire_type == 0) tick_count = (unsigned int)g.varint; }
+    } else if (f.number == 2) configs.push_back(NetConfig::parse(f.data, f.size));
+    else if (f.number == 3) { run_whiskers = WhiskerTree::parse(f.data, f.size); have_tree = true; }
+  }
+  if (!have_tree) throw std::runtime_error("Problem has no whiskers");
+  return score(run_whiskers, prng_seed, configs, false, tick_count);
+}
+
+std::string Evaluator<WhiskerTree>::Outcome::DNA() const
+{ /* src/evaluator.cc:162-180 */
+  pb::Writer w;
+  for (const auto &run : throughputs_delays) {
+    pb::Writer td;
+    td.put_message(21, run.first.DNA());
+    for (const auto &x : run.second) { pb::Writer r; r.put_double(11, x.first); r.put_double(12, x.second); td.put_message(22, r.str()); }
+    w.put_message(32, td.str());
+  }
+  w.put_double(33, score);
+  return w.str();
+}
+
+Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::Outcome::parse(const void *data, size_t size)
+{ /* src/evaluator.cc:182-194 */
+  Outcome o;
+  pb::Reader rd(data, size); pb::Field f;
+  while (rd.next(f)) {
+    if (f.number == 33 && f.wire_type == 1) o.score = pb::Reader::as_double(f);
+    else if (f.number == 32 && f.wire_type == 2) {
+      NetConfig cfg; std::vector<std::pair<double, double>> td;
+      pb::Reader tr(f.data, f.size); pb::Field g;
+      while (tr.next(g)) {
+        if (g.number == 21 && g.wire_type == 2) cfg = NetConfig::parse(g.data, g.size);
+        else if (g.number == 22 && g.wire_type == 2) {
+          double tp = 0, dl = 0;
+          pb::Reader rr(g.data, g.size); pb::Field h;
+          while (rr.next(h)) { if (h.number == 11 && h.wire_type == 1) tp = pb::Reader::as_double(h); else if (h.number == 12 && h.wire_type == 1) dl = pb::Reader::as_double(h); }
+          td.emplace_back(tp, dl);
+        }
+      }
+      o.throughputs_delays.emplace_back(cfg, td);
+    }
+  }
+  return o;
 }
 
 std::vector<double> Evaluator<WhiskerTree>::score_candidates(const WhiskerTree &base, const std::vector<Whisker> &replacements,

@@ -63,6 +63,8 @@ public:
   NetConfig &set_stochastic_loss_rate(double v) { stochastic_loss_rate = v; return *this; }
   NetConfig &set_simulation_ticks(unsigned int n) { simulation_ticks = n; return *this; }
   std::string str() const;
+  std::string DNA() const;                         /* RemyBuffers.NetConfig bytes (src/network.hh:57-70) */
+  static NetConfig parse(const void *data, size_t size);
   RemyNetConfig pod(double ticks_to_run) const;  /* the conversions of src/network.cc:24-37 */
 };
 
@@ -184,6 +186,9 @@ public:
     double score = 0;
     std::vector<std::pair<NetConfig, std::vector<std::pair<double, double>>>> throughputs_delays;
     WhiskerTree used_actions;
+    Outcome() {}
+    std::string DNA() const;                              /* AnswerBuffers.Outcome bytes (src/evaluator.cc:162-180) */
+    static Outcome parse(const void *data, size_t size);  /* Outcome(AnswerBuffers::Outcome) (src/evaluator.cc:182-194) */
   };
 private:
   unsigned int _prng_seed;
@@ -201,6 +206,10 @@ public:
   /* The data-parallel replacement for ActionImprover::evaluate_replacements
    * (src/breeder.cc:53-77): scores[c] = score of `tree` with replacements[c] applied. */
   std::vector<double> score_candidates(const WhiskerTree &tree, const std::vector<Whisker> &replacements, double carefulness = 1) const;
+  /* ProblemBuffers.Problem bytes: settings {prng_seed, tick_count}, configs, whiskers (src/evaluator.cc:40-66) */
+  std::string DNA(const WhiskerTree &whiskers) const;
+  /* src/evaluator.cc:134-146 */
+  static Outcome parse_problem_and_evaluate(const void *problem, size_t size);
   /* per-config seeds of a score() call: prng_seed itself for config 0 (as in the reference), then the
    * successive outputs of minstd_rand0(prng_seed) */
   static std::vector<uint32_t> seeds(unsigned int prng_seed, size_t n);

@@ -31,6 +31,11 @@ class HostLib:
         L.remy_host_config_range_expand.argtypes = [C.c_char_p, C.c_size_t, C.c_double, _V, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_long)]
         L.remy_host_evaluator_score.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.POINTER(C.c_double), _V, C.c_uint32,
                                                 _V, C.c_uint32, C.POINTER(C.c_uint32)]
+        for name in ("remy_host_solve_problem", "remy_host_answer_roundtrip"):
+            getattr(L, name).restype = C.c_long
+            getattr(L, name).argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.remy_host_problem_dna.restype = C.c_long
+        L.remy_host_problem_dna.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_char_p, C.c_size_t]
         L.remy_host_improve_whisker.restype = C.c_long
         L.remy_host_improve_whisker.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint32, _V]
         L.remy_host_ratbreeder_improve.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_double), _V]
@@ -56,6 +61,20 @@ class HostLib:
         h = self.lib.remy_host_tree_from_flat(flat.byref())
         self._check(h)
         return HostTree(self, h)
+
+    def _bytes_call(self, fn, *args):
+        n = fn(*args, None, 0)
+        self._check(n >= 0)
+        buf = C.create_string_buffer(n + 1)
+        self._check(fn(*args, buf, n) == n)
+        return buf.raw[:n]
+
+    def solve_problem(self, problem):
+        """Evaluator::parse_problem_and_evaluate -> AnswerBuffers.Outcome bytes (needs a GPU)."""
+        return self._bytes_call(self.lib.remy_host_solve_problem, problem, len(problem))
+
+    def answer_roundtrip(self, answer):
+        return self._bytes_call(self.lib.remy_host_answer_roundtrip, answer, len(answer))
 
     def expand(self, range_bytes, carefulness=1.0):
         out = np.zeros(1 << 16, dtype=abi.net_config_dtype)
@@ -113,6 +132,10 @@ class HostTree:
                                                       counts.ctypes.data, len(counts), td.ctypes.data, len(td), C.byref(n_td))
         self.host._check(rc == 0)
         return score.value, counts, td[:n_td.value].reshape(-1, 2).copy()
+
+    def problem_dna(self, range_bytes, prng_seed):
+        """Evaluator::DNA(tree) -> ProblemBuffers.Problem bytes."""
+        return self.host._bytes_call(self.host.lib.remy_host_problem_dna, self.h, range_bytes, len(range_bytes), prng_seed)
 
     def improve_whisker(self, range_bytes, prng_seed, leaf):
         """WhiskerImprover::improve repeated until the score stops rising -> (calls, score, (incr, mult, intersend), candidates, batches)."""

@@ -181,3 +181,36 @@ def test_whisker_improver_matches_oracle_driven_restatement(host, oracle):
     assert calls == py_calls and action == w, (calls, py_calls, action, w)
     assert abs(score - to_beat) <= 1e-9 * abs(to_beat)
     assert batches <= 2 * calls and n_scored >= 80          # two batch calls per improve(), not one thread per candidate
+
+
+def test_parse_problem_and_evaluate(host, oracle):
+    """The Problem -> Answer wire path (src/evaluator.cc:134-146, src/scoring-example.cc): a Problem
+    written by Evaluator::DNA is solved on the GPU; the Answer's score and per-sender numbers equal
+    what the oracle gives for the Problem's configs, seed and tick count."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import pb_schema
+    cls = pb_schema.classes()
+    flat = workloads.load_golden_tree("RemyCC-2013-delta1")
+    tree = host.tree_from_flat(flat)
+    inf = float(abi.BUFFER_INFINITE)
+    raw_range = hostlib.encode_config_range(link=(1, 2, 1), rtt=(100, 200, 100), nsrc=(2, 10, 8), buf=(inf, inf, 0),
+                                            off=(3000, 3000, 0), on=(3000, 3000, 0), ticks=15000)
+    problem = tree.problem_dna(raw_range, 31337)
+    answer = host.solve_problem(problem)
+    a = cls["Outcome"]()
+    a.ParseFromString(answer)
+    assert a.SerializeToString() == answer
+    cfgs, _ = host.expand(raw_range)
+    sims, snd, _ = oracle.score(flat, cfgs, workloads.seeds_for(31337, len(cfgs)), threads=8)
+    want = 0.0
+    for u in sims["utility"]:
+        want += float(u)
+    assert abs(a.score - want) <= 1e-9 * abs(want)
+    assert len(a.throughputs_delays) == len(cfgs)
+    for k, td in enumerate(a.throughputs_delays):
+        assert td.config.link_ppt == cfgs[k]["link_ppt"] and td.config.num_senders == cfgs[k]["num_senders"]
+        for s, r in enumerate(td.results):
+            x = snd[k][s]
+            assert r.throughput == (0.0 if x["tick_share_sending"] == 0 else float(x["packets_received"]) / x["tick_share_sending"])
+            assert r.delay == (0.0 if x["packets_received"] == 0 else x["total_delay"] / float(x["packets_received"]))
