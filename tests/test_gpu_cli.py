@@ -51,3 +51,41 @@ def test_sender_runner_verify_2014_10(built, device, oracle, tmp_path):
     # (the tree was re-serialised from the golden POD arrays, so it carries no config/optimizer
     # sub-messages and print_tree prints nothing; tests/test_host.py covers the real .dna files)
     assert out.stdout.startswith("score = ")
+
+
+def test_remy_cli_writes_checkpoints(built, device, tmp_path):
+    """`remy cf=... of=... opt=bmr runs=1` (src/remy.cc): banner, per-config report, and a checkpoint
+    `<of>.0` that is a RemyBuffers.WhiskerTree carrying config, optimizer and configvector, readable by
+    a real protobuf implementation and by sender-runner."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import pb_schema
+    built.build_host()
+    inf = float(abi.BUFFER_INFINITE)
+    cfg_path = tmp_path / "range.cfg"
+    cfg_path.write_bytes(hostlib.encode_config_range(link=(1, 2, 1), rtt=(100, 100, 0), nsrc=(2, 6, 4), buf=(inf, inf, 0),
+                                                     off=(1000, 1000, 0), on=(1000, 1000, 0), ticks=4000))
+    exe = os.path.join(ROOT, "remy_b200", "host", "remy")
+    of = tmp_path / "cc"
+    out = subprocess.run([exe, f"cf={cfg_path}", f"of={of}", "opt=bmr", "runs=1", "seed=3"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Evaluator simulations will run for 4000 ticks" in out.stdout
+    assert "Optimizing window increment: 1, window multiple: 1, intersend: 1" in out.stdout
+    assert "Optimizing for link packets_per_ms over [1.000000 : 1.000000 : 2.000000]" in out.stdout
+    assert "Optimizing for infinitely sized buffers." in out.stdout
+    assert re.search(r"^run = 0, score = -?[0-9.]+$", out.stdout, re.M)
+    assert out.stdout.count("config: mean_on=1000.000000") == 4 and out.stdout.count("sender: [tp=") == 2 * (2 + 6)
+    raw = (tmp_path / "cc.0").read_bytes()
+    msg = pb_schema.classes()["WhiskerTree"]()
+    msg.ParseFromString(raw)
+    assert msg.SerializeToString() == raw
+    assert msg.config.simulation_ticks == 4000 and msg.config.num_senders.high == 6
+    assert msg.optimizer.intersend.min_value == 0.25 and msg.optimizer.window_increment.max_value == 256
+    assert len(msg.configvector.config) == 4 and msg.HasField("leaf")
+    leaf = msg.leaf
+    assert 0 <= leaf.window_increment <= 256 and 0 <= leaf.window_multiple <= 1 and 0.25 <= leaf.intersend <= 3
+    # the optimiser only ever accepts strict improvements, and the checkpoint feeds straight back into sender-runner
+    assert "Regression" not in out.stderr or "Ending search." in out.stderr
+    sr = subprocess.run([os.path.join(ROOT, "remy_b200", "host", "sender-runner"), f"if={of}.0", "nsrc=2", "link=1", "rtt=100",
+                         "seed=1", "ticks=2000"], capture_output=True, text=True, timeout=300)
+    assert sr.returncode == 0 and sr.stdout.startswith("Prior assumptions:\nlink_packets_per_ms {\n  low: 1\n  high: 2\n  incr: 1\n}")
