@@ -178,6 +178,35 @@ void remy_b200_batch_destroy(RemyBatch *batch);
 /* Number of kernel launches performed by the last remy_b200_batch_run. */
 uint32_t remy_b200_batch_launches(const RemyBatch *batch);
 
+/* ---- trace == true scoring ------------------------------------------------ *
+ * Replaces: Evaluator<WhiskerTree>::score(tree, trace = true) (src/evaluator.cc:77-103 with
+ * Rat::_track set, src/rat.cc:8-20), the call Breeder::apply_best_split makes
+ * (src/breeder.cc:21) to learn, for every whisker, the running medians of the Memory values
+ * it was asked about (MemoryRange::track, src/memoryrange.cc:60-66; used by
+ * MemoryRange::bisect, :8-41).  The estimators themselves (Boost's P^2 median, order
+ * dependent) live on the host side of this boundary; the device returns what they are fed:
+ * one record per WhiskerTree::use_whisker call (src/whiskertree.cc:42-60), in the exact order
+ * the reference makes the calls within a simulation.
+ *
+ *   record = words_per_record 64-bit words: { leaf index,
+ *            bit pattern of Memory::field(a) for every axis a that is active anywhere in
+ *            the tree, ascending a }          (words_per_record = 1 + number of such axes)
+ *
+ * `sink` is called on the calling thread, with cfg_index ascending; the records of one
+ * config arrive in simulation order, possibly split over several calls (the buffer is only
+ * valid during the call).  A non-zero return from the sink aborts with REMY_EINVAL.
+ * out_* as in remy_b200_score_batch with n_cands == 1.  If any simulation ends with an error
+ * word the results are returned but no records are delivered.
+ */
+typedef int (*RemyTraceSink)(void *user, uint32_t cfg_index, const uint64_t *records,
+                             uint64_t n_records, uint32_t words_per_record);
+
+int remy_b200_score_trace(const RemyFlatTree *tree,
+                          const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                          uint32_t sender_stride,
+                          RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
+                          RemyTraceSink sink, void *user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -266,3 +266,100 @@ extern "C" void remy_ref_shuffle(uint32_t *state, uint32_t *idx, uint32_t n)
   std::ostringstream os; os << g; *state = (uint32_t)std::stoul(os.str());
 }
 extern "C" double remy_ref_log(double x) { return std::log(x); }
+
+/* ---- trace == true: per-leaf running medians, and Breeder::apply_best_split ------------- *
+ * The reference's own Evaluator::score(..., trace = true, ...), MemoryRange::track / bisect,
+ * WhiskerTree::most_used, WhiskerTree(whisker, bisect = true) and replace(src, dst) run here;
+ * only the 20-line control flow of Breeder::apply_best_split (src/breeder.cc:15-41, dead in
+ * the fork because of its leading assert(false)) is re-stated around them.  Scoring follows
+ * the batched evaluator's contract: the static score() once per config with seeds[k], on ONE
+ * tree object, so every leaf's accumulators see config 0's lookups, then config 1's, ...;
+ * use counts are summed over the calls (each call starts with reset_counts()). */
+namespace {
+
+void collect_leaves(WhiskerTree &t, std::vector<Whisker *> &out)
+{
+  if (t.is_leaf()) { out.push_back(&t._leaf.front()); return; }
+  for (auto &c : t._children) collect_leaves(c, out);
+}
+
+void flatten_tree(const WhiskerTree &t, std::vector<RemyTreeNode> &nodes, std::vector<RemyLeafAction> &leaves, uint32_t self)
+{
+  RemyTreeNode nd; memset(&nd, 0, sizeof nd);
+  for (unsigned a = 0; a < REMY_NUM_AXES; a++) { nd.lower[a] = t._domain._lower.field(a); nd.upper[a] = t._domain._upper.field(a); }
+  for (auto a : t._domain._active_axis) nd.axis_mask |= 1u << (unsigned)a;
+  if (t.is_leaf()) {
+    const Whisker &w = t._leaf.front();
+    nd.child_count = 0; nd.leaf_index = (uint32_t)leaves.size();
+    RemyLeafAction la; la.window_multiple = w._window_multiple; la.intersend = w._intersend;
+    la.window_increment = w._window_increment; la.generation = w._generation;
+    leaves.push_back(la);
+    nodes[self] = nd;
+    return;
+  }
+  nd.child_begin = (uint32_t)nodes.size(); nd.child_count = (uint32_t)t._children.size();
+  nodes[self] = nd;
+  nodes.resize(nodes.size() + t._children.size());
+  for (size_t c = 0; c < t._children.size(); c++) flatten_tree(t._children[c], nodes, leaves, nd.child_begin + (uint32_t)c);
+}
+
+} // namespace
+
+extern "C" int remy_ref_trace_split(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                    uint32_t generation, int do_split,
+                                    double *out_medians /* [n_leaves][REMY_NUM_AXES] */, uint32_t *out_use_counts /* [n_leaves] */,
+                                    double *out_score,
+                                    RemyTreeNode *out_nodes, uint32_t node_cap, RemyLeafAction *out_leaves, uint32_t leaf_cap,
+                                    uint32_t *out_n_nodes, uint32_t *out_n_leaves)
+{
+  RemyBuffers::WhiskerTree dna;
+  build_dna(tree, 0, nullptr, &dna);
+  WhiskerTree t(dna);
+  {
+    std::vector<Whisker *> lv; collect_leaves(t, lv);
+    for (size_t l = 0; l < lv.size() && l < tree->n_leaves; l++) lv[l]->_generation = tree->leaves[l].generation;
+  }
+  std::vector<unsigned> sums(tree->n_leaves, 0);
+  double score = 0;
+  for (uint32_t k = 0; k < n_cfgs; k++) {
+    std::vector<NetConfig> one { to_netconfig(cfgs[k]) };
+    auto outcome = Evaluator<WhiskerTree>::score(t, seeds[k], one, true, (unsigned int)cfgs[k].simulation_ticks);
+    score += outcome.score;
+    std::vector<unsigned> counts; collect_counts(t, counts);
+    for (size_t l = 0; l < counts.size(); l++) sums[l] += counts[l];
+  }
+  std::vector<Whisker *> lv; collect_leaves(t, lv);
+  for (size_t l = 0; l < lv.size(); l++) {
+    lv[l]->_domain._count = sums[l];
+    if (out_use_counts) out_use_counts[l] = sums[l];
+    if (out_medians)
+      for (unsigned a = 0; a < REMY_NUM_AXES; a++) out_medians[l * REMY_NUM_AXES + a] = boost::accumulators::median(lv[l]->_domain._acc[a]);
+  }
+  if (out_score) *out_score = score;
+  if (do_split) { /* src/breeder.cc:21-40 with outcome.used_actions == a copy of the scored tree */
+    WhiskerTree used_actions(t);
+    while (1) {
+      auto my_action(used_actions.most_used(generation));
+      if (!my_action) return -2;
+      WhiskerTree bisected_action(*my_action, true);
+      if (bisected_action.num_children() == 1) {
+        auto mutable_action(*my_action);
+        mutable_action.promote(generation + 1);
+        if (!used_actions.replace(mutable_action)) return -3;
+        continue;
+      }
+      if (!t.replace(*my_action, bisected_action)) return -4;
+      break;
+    }
+  }
+  std::vector<RemyTreeNode> nodes(1); std::vector<RemyLeafAction> leaves;
+  flatten_tree(t, nodes, leaves, 0);
+  if (out_n_nodes) *out_n_nodes = (uint32_t)nodes.size();
+  if (out_n_leaves) *out_n_leaves = (uint32_t)leaves.size();
+  if (out_nodes && out_leaves) {
+    if (nodes.size() > node_cap || leaves.size() > leaf_cap) return REMY_EINVAL;
+    memcpy(out_nodes, nodes.data(), nodes.size() * sizeof(RemyTreeNode));
+    memcpy(out_leaves, leaves.data(), leaves.size() * sizeof(RemyLeafAction));
+  }
+  return 0;
+}

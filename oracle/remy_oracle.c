@@ -179,6 +179,10 @@ typedef struct {
   const RemyFlatTree *tree;
   const RemyLeafOverride *ov; /* may be NULL */
   uint32_t *use_counts;       /* may be NULL; [n_leaves] */
+  /* trace == true (Rat::_track, src/rat.hh:22): every use_whisker call reports the leaf it
+   * returned and the Memory it was asked about (MemoryRange::track, src/memoryrange.cc:60-66) */
+  void (*track)(void *user, uint32_t leaf, const double *mem);
+  void *track_user;
 } policy_t;
 
 /* MemoryRange::contains (src/memoryrange.cc:52-58). */
@@ -215,6 +219,7 @@ static int use_whisker(const policy_t *pol, const memory_t *m, RemyLeafAction *o
     out->intersend = pol->ov->intersend;
   }
   if (pol->use_counts) pol->use_counts[leaf]++;
+  if (pol->track) pol->track(pol->track_user, leaf, m->f); /* whiskertree.cc:55-57 */
   return 1;
 }
 
@@ -453,10 +458,25 @@ static double utility_value(const utility_t *u)
 /* One simulation: Network ctor (src/network.cc:24-37), SenderGang ctor
  * (src/sendergang.cc:9-26), run_simulation (src/network.cc:63-85), then
  * SenderGang::utility (src/sendergang.cc:280-293). */
+void remy_oracle_run_sim_traced(const RemyFlatTree *tree, const RemyLeafOverride *ov,
+                                const RemyNetConfig *cfg, uint32_t seed,
+                                RemySimResult *out, RemySenderResult *out_senders,
+                                uint32_t *use_counts,
+                                void (*track)(void *, uint32_t, const double *), void *track_user);
+
 void remy_oracle_run_sim(const RemyFlatTree *tree, const RemyLeafOverride *ov,
                          const RemyNetConfig *cfg, uint32_t seed,
                          RemySimResult *out, RemySenderResult *out_senders,
                          uint32_t *use_counts)
+{
+  remy_oracle_run_sim_traced(tree, ov, cfg, seed, out, out_senders, use_counts, NULL, NULL);
+}
+
+void remy_oracle_run_sim_traced(const RemyFlatTree *tree, const RemyLeafOverride *ov,
+                                const RemyNetConfig *cfg, uint32_t seed,
+                                RemySimResult *out, RemySenderResult *out_senders,
+                                uint32_t *use_counts,
+                                void (*track)(void *, uint32_t, const double *), void *track_user)
 {
   memset(out, 0, sizeof *out);
   if (cfg->num_senders == 0 || cfg->num_senders > 4096 || !(cfg->simulation_ticks > 0)
@@ -469,6 +489,7 @@ void remy_oracle_run_sim(const RemyFlatTree *tree, const RemyLeafOverride *ov,
   N.pol.tree = tree;
   N.pol.ov = (ov && ov->leaf_index != REMY_NO_OVERRIDE) ? ov : NULL;
   N.pol.use_counts = use_counts;
+  N.pol.track = track; N.pol.track_user = track_user;
   N.n = cfg->num_senders;
   N.gang = (sender_t *)calloc(N.n, sizeof(sender_t));
   N.collector = (mailbox_t *)calloc(N.n, sizeof(mailbox_t));
@@ -610,3 +631,108 @@ uint32_t remy_oracle_prng_next(uint32_t x) { prng_t g = { x }; return prng_next(
 double remy_oracle_canonical(uint32_t *state) { prng_t g = { *state }; double r = prng_canonical(&g); *state = g.x; return r; }
 double remy_oracle_exponential(uint32_t *state, double rate) { prng_t g = { *state }; double r = exp_sample(&g, rate); *state = g.x; return r; }
 void remy_oracle_shuffle(uint32_t *state, uint32_t *idx, uint32_t n) { prng_t g = { *state }; shuffle_indices(&g, idx, n); *state = g.x; }
+
+/* ----------------------------------------------------- trace == true ---- */
+/* boost::accumulators::accumulator_set<double, stats<tag::median>> as used by
+ * MemoryRange::_acc (src/memoryrange.hh:24-26): tag::median is the P^2 running estimator
+ * (Jain & Chlamtac 1985) for p = 0.5, NOT an exact median.  Boost is a third-party
+ * dependency that is absent from /root/reference and from this image (the reference pins no
+ * version, configure.ac:57-59); this restates the published algorithm in the form of
+ * boost/accumulators/statistics/p_square_quantile.hpp (1.5x-1.8x: unchanged in that range):
+ * first five samples stored and sorted, then per sample: find the cell, shift marker
+ * positions, advance desired positions by {0, p/2, p, (1+p)/2, 1}, and move markers 1..3 by
+ * +-1 with the piecewise-parabolic formula (linear if it would leave the bracket).
+ * "Parity unpinned" for this estimator: no Boost here to run against. */
+typedef struct { double h[5], n[5], d[5], inc[5]; uint64_t count; } p2_t;
+
+void remy_oracle_p2_init(p2_t *a)
+{
+  const double p = 0.5;
+  for (int i = 0; i < 5; i++) { a->h[i] = 0; a->n[i] = i + 1.; }
+  a->d[0] = 1.; a->d[1] = 1. + 2. * p; a->d[2] = 1. + 4. * p; a->d[3] = 3. + 2. * p; a->d[4] = 5.;
+  a->inc[0] = 0.; a->inc[1] = p / 2.; a->inc[2] = p; a->inc[3] = (1. + p) / 2.; a->inc[4] = 1.;
+  a->count = 0;
+}
+
+void remy_oracle_p2_add(p2_t *a, double x)
+{
+  const uint64_t cnt = ++a->count;
+  if (cnt <= 5) {
+    a->h[cnt - 1] = x;
+    if (cnt == 5) { /* std::sort of five values */
+      for (int i = 1; i < 5; i++) { const double v = a->h[i]; int j = i; while (j > 0 && v < a->h[j - 1]) { a->h[j] = a->h[j - 1]; j--; } a->h[j] = v; }
+    }
+    return;
+  }
+  unsigned k;
+  if (x < a->h[0]) { a->h[0] = x; k = 1; }
+  else if (a->h[4] <= x) { a->h[4] = x; k = 4; }
+  else { k = 0; while (k < 5 && !(x < a->h[k])) k++; } /* std::upper_bound */
+  for (unsigned i = k; i < 5; i++) a->n[i] += 1.;
+  for (unsigned i = 0; i < 5; i++) a->d[i] += a->inc[i];
+  for (unsigned i = 1; i <= 3; i++) {
+    const double d = a->d[i] - a->n[i];
+    const double dp = a->n[i + 1] - a->n[i];
+    const double dm = a->n[i - 1] - a->n[i];
+    const double hp = (a->h[i + 1] - a->h[i]) / dp;
+    const double hm = (a->h[i - 1] - a->h[i]) / dm;
+    if ((d >= 1. && dp > 1.) || (d <= -1. && dm < -1.)) {
+      const short sign_d = (short)(d / fabs(d));
+      const double h = a->h[i] + sign_d / (dp - dm) * ((sign_d - dm) * hp + (dp - sign_d) * hm);
+      if (a->h[i - 1] < h && h < a->h[i + 1]) a->h[i] = h;
+      else {
+        if (d > 0) a->h[i] += hp;
+        if (d < 0) a->h[i] -= hm;
+      }
+      a->n[i] += sign_d;
+    }
+  }
+}
+
+double remy_oracle_p2_median(const p2_t *a) { return a->h[2]; }
+
+/* Raw trace of one simulation: record k = { (double)leaf, mem[0..5] } at out[7k..7k+6], in the
+ * order of the use_whisker calls.  Returns the number of calls (records beyond `cap` are
+ * counted but not stored). */
+typedef struct { double *out; uint64_t cap, n; } trace_log_t;
+static void trace_log_cb(void *user, uint32_t leaf, const double *mem)
+{
+  trace_log_t *t = (trace_log_t *)user;
+  if (t->n < t->cap) { double *r = t->out + 7 * t->n; r[0] = (double)leaf; for (int a = 0; a < REMY_NUM_AXES; a++) r[1 + a] = mem[a]; }
+  t->n++;
+}
+uint64_t remy_oracle_trace_sim(const RemyFlatTree *tree, const RemyNetConfig *cfg, uint32_t seed,
+                               RemySimResult *out_sim, double *out, uint64_t cap)
+{
+  trace_log_t t = { out, cap, 0 };
+  RemySimResult tmp;
+  remy_oracle_run_sim_traced(tree, NULL, cfg, seed, out_sim ? out_sim : &tmp, NULL, NULL, trace_log_cb, &t);
+  return t.n;
+}
+
+/* Evaluator::score(tree, seed_k, {config_k}, trace = true, ticks) for k = 0..n_cfgs-1 on ONE
+ * tree object, i.e. every leaf's accumulators see the lookups of config 0, then config 1, ...
+ * (MemoryRange::track feeds _acc[axis] for the leaf's active axes, src/memoryrange.cc:60-66).
+ * acc: [n_leaves][REMY_NUM_AXES] estimators, carried in and out (NULL-initialised by the caller
+ * with remy_oracle_p2_init). */
+typedef struct { const RemyFlatTree *tree; const uint32_t *leaf_axes; p2_t *acc; } trace_acc_t;
+static void trace_acc_cb(void *user, uint32_t leaf, const double *mem)
+{
+  trace_acc_t *t = (trace_acc_t *)user;
+  for (int a = 0; a < REMY_NUM_AXES; a++)
+    if (t->leaf_axes[leaf] & (1u << a)) remy_oracle_p2_add(&t->acc[(size_t)leaf * REMY_NUM_AXES + a], mem[a]);
+}
+int remy_oracle_trace_medians(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                              RemySimResult *out_sims, uint32_t *out_use_counts, p2_t *acc)
+{
+  uint32_t *leaf_axes = (uint32_t *)calloc(tree->n_leaves, sizeof(uint32_t));
+  for (uint32_t i = 0; i < tree->n_nodes; i++)
+    if (tree->nodes[i].child_count == 0) leaf_axes[tree->nodes[i].leaf_index] = tree->nodes[i].axis_mask;
+  trace_acc_t t = { tree, leaf_axes, acc };
+  if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * tree->n_leaves);
+  for (uint32_t k = 0; k < n_cfgs; k++)
+    remy_oracle_run_sim_traced(tree, NULL, &cfgs[k], seeds[k], &out_sims[k], NULL, out_use_counts, trace_acc_cb, &t);
+  free(leaf_axes);
+  return 0;
+}
+size_t remy_oracle_p2_sizeof(void) { return sizeof(p2_t); }

@@ -152,6 +152,42 @@ class Oracle(_ScoreLib):
     def score(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1):
         return super().score(tree, cfgs, seeds, cands, want_senders, want_use_counts, extra=(threads,))
 
+    def trace_sim(self, tree, cfg, seed, cap=1 << 22):
+        """Every use_whisker call of one simulation, in call order: (sim result, leaf[n], mem[n, 6])."""
+        f = self.lib.remy_oracle_trace_sim
+        f.restype = C.c_uint64
+        f.argtypes = [C.POINTER(FlatTreeC), _PTR, C.c_uint32, _PTR, _PTR, C.c_uint64]
+        cfg = np.ascontiguousarray(cfg, dtype=net_config_dtype).reshape(1)
+        sim = np.zeros(1, dtype=sim_result_dtype)
+        buf = np.zeros(cap * 7, dtype=np.float64)
+        n = int(f(tree.byref(), _ptr(cfg), int(seed), _ptr(sim), _ptr(buf), cap))
+        if n > cap:
+            return self.trace_sim(tree, cfg, seed, cap=n)
+        rec = buf[:n * 7].reshape(n, 7)
+        return sim[0], rec[:, 0].astype(np.uint32), np.ascontiguousarray(rec[:, 1:])
+
+    def trace_medians(self, tree, cfgs, seeds):
+        """score(tree, seeds[k], {cfgs[k]}, trace=true) for k = 0.. on one tree -> (sims, use counts,
+        medians[n_leaves, 6]) of the P^2 estimators MemoryRange::track feeds."""
+        L = self.lib
+        L.remy_oracle_p2_sizeof.restype = C.c_size_t
+        sz = L.remy_oracle_p2_sizeof()
+        L.remy_oracle_p2_init.argtypes = [_PTR]
+        L.remy_oracle_p2_median.argtypes = [_PTR]
+        L.remy_oracle_p2_median.restype = C.c_double
+        L.remy_oracle_trace_medians.argtypes = [C.POINTER(FlatTreeC), _PTR, _PTR, C.c_uint32, _PTR, _PTR, _PTR]
+        cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        nl = tree.n_leaves
+        acc = np.zeros(nl * NUM_AXES * sz, dtype=np.uint8)
+        for i in range(nl * NUM_AXES):
+            L.remy_oracle_p2_init(acc.ctypes.data + i * sz)
+        sims = np.zeros(len(cfgs), dtype=sim_result_dtype)
+        counts = np.zeros(nl, dtype=np.uint32)
+        L.remy_oracle_trace_medians(tree.byref(), _ptr(cfgs), _ptr(seeds), len(cfgs), _ptr(sims), _ptr(counts), _ptr(acc))
+        med = np.array([L.remy_oracle_p2_median(acc.ctypes.data + i * sz) for i in range(nl * NUM_AXES)]).reshape(nl, NUM_AXES)
+        return sims, counts, med
+
 
 class Reference(_ScoreLib):
     """oracle/_ref/libremy_ref.so — the reference's own sources (test infrastructure)."""
@@ -162,6 +198,27 @@ class Reference(_ScoreLib):
 
     def score(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1, mode=0):
         return super().score(tree, cfgs, seeds, cands, want_senders, want_use_counts, extra=(threads, mode))
+
+    def trace_split(self, tree, cfgs, seeds, generation=0, split=True):
+        """The reference's own trace == true scoring (per config, on one tree) and, if `split`, the
+        body of Breeder::apply_best_split -> (score, use counts, medians[n_leaves, 6], resulting FlatTree)."""
+        f = self.lib.remy_ref_trace_split
+        f.argtypes = [C.POINTER(FlatTreeC), _PTR, _PTR, C.c_uint32, C.c_uint32, C.c_int, _PTR, _PTR, C.POINTER(C.c_double),
+                      _PTR, C.c_uint32, _PTR, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        med = np.zeros((tree.n_leaves, NUM_AXES))
+        counts = np.zeros(tree.n_leaves, dtype=np.uint32)
+        score = C.c_double()
+        cap = len(tree.nodes) + 4096
+        nodes = np.zeros(cap, dtype=tree_node_dtype)
+        leaves = np.zeros(cap, dtype=leaf_action_dtype)
+        nn, nl = C.c_uint32(), C.c_uint32()
+        rc = f(tree.byref(), _ptr(cfgs), _ptr(seeds), len(cfgs), generation, int(split), _ptr(med), _ptr(counts), C.byref(score),
+               _ptr(nodes), cap, _ptr(leaves), cap, C.byref(nn), C.byref(nl))
+        if rc != 0:
+            raise RuntimeError(f"remy_ref_trace_split returned {rc}")
+        return score.value, counts, med, FlatTree(nodes[:nn.value].copy(), leaves[:nl.value].copy())
 
 
 class Device(_ScoreLib):
@@ -193,6 +250,38 @@ class Device(_ScoreLib):
 
     def last_error(self):
         return self.lib.remy_b200_last_error().decode()
+
+    def score_trace(self, tree, cfgs, seeds):
+        """remy_b200_score_trace -> (sims, senders, use counts, [(leaf[n], values[n, words - 1]) per config])."""
+        sink_t = C.CFUNCTYPE(C.c_int, _PTR, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32)
+        f = self.lib.remy_b200_score_trace
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(FlatTreeC), _PTR, _PTR, C.c_uint32, C.c_uint32, _PTR, _PTR, _PTR, sink_t, _PTR]
+        cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        stride = max(1, int(cfgs["num_senders"].max())) if len(cfgs) else 1
+        sims = np.zeros(len(cfgs), dtype=sim_result_dtype)
+        senders = np.zeros((len(cfgs), stride), dtype=sender_result_dtype)
+        counts = np.zeros((1, tree.n_leaves), dtype=np.uint32)
+        chunks = [[] for _ in range(len(cfgs))]
+        order = []
+
+        def sink(_user, k, rec, n, words):
+            order.append(k)
+            if n:
+                chunks[k].append(np.ctypeslib.as_array(rec, shape=(n * words,)).reshape(n, words).copy())
+            return 0
+
+        cb = sink_t(sink)
+        rc = f(tree.byref(), _ptr(cfgs), _ptr(seeds), len(cfgs), stride, _ptr(sims), _ptr(senders), _ptr(counts), cb, None)
+        if rc != 0:
+            raise RuntimeError(f"remy_b200_score_trace failed with {rc}: {self.last_error()}")
+        assert order == sorted(order)
+        out = []
+        for c in chunks:
+            a = np.concatenate(c) if c else np.zeros((0, 1), dtype=np.uint64)
+            out.append((a[:, 0].astype(np.uint32), np.ascontiguousarray(a[:, 1:]).view(np.float64)))
+        return sims, senders, counts, out
 
     def create_batch(self, tree, cfgs, seeds, cands=None, want_senders=False, want_use_counts=False):
         return DeviceBatch(self, tree, cfgs, seeds, cands, want_senders, want_use_counts)

@@ -98,6 +98,9 @@ struct RemyBatch {
   DevBuf<RemySimResult> out_sims; DevBuf<RemySenderResult> out_senders; DevBuf<uint32_t> out_counts;
   std::vector<std::unique_ptr<Pass>> passes;
   uint32_t launches = 0;
+  /* trace == true scoring (remy_b200_score_trace): 0 = off, 1 = counting run, 2 = writing run */
+  int trace = 0; uint32_t trace_words = 0;
+  DevBuf<uint64_t> trace_log, trace_off, out_lookups;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ran = false;
   ~RemyBatch()
@@ -117,6 +120,7 @@ size_t smem_bytes(const RemyBatch *b, uint32_t n_max, bool with_tree)
 
 const void *kernel_fn(const RemyBatch *b)
 {
+  if (b->trace) return (const void *)remy_sim_kernel<true, true>;
   return b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
 }
 
@@ -132,6 +136,8 @@ KernelArgs make_args(RemyBatch *b, const Scratch &s, bool tree_in_smem, const ui
   a.delay_ring = s.delay.p; a.delay_cap = s.delay_cap; a.slot_counts = s.counts.p;
   a.out_sims = b->out_sims.p; a.out_senders = b->want_senders ? b->out_senders.p : nullptr;
   a.sender_stride = b->sender_stride; a.out_use_counts = b->want_counts ? b->out_counts.p : nullptr;
+  a.trace_log = b->trace == 2 ? b->trace_log.p : nullptr; a.trace_off = b->trace == 2 ? b->trace_off.p : nullptr;
+  a.out_lookups = b->trace ? b->out_lookups.p : nullptr; a.trace_words = b->trace_words;
   return a;
 }
 
@@ -197,7 +203,8 @@ int launch(RemyBatch *b, const Scratch &s, size_t smem, bool tree_in_smem, const
 {
   CU(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
   const KernelArgs a = make_args(b, s, tree_in_smem, order, n_work, counter);
-  if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  if (b->trace) remy_sim_kernel<true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else remy_sim_kernel<false><<<grid, SIM_BLOCK, smem, stream>>>(a);
   CU(cudaGetLastError());
   b->launches++;
@@ -234,6 +241,7 @@ int remy_b200_init(int device)
   /* the kernel stages the tree in shared memory: allow the large carve-out */
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_device = device; g_sms = prop.multiProcessorCount;
   g_err.clear();
   return 0;
@@ -249,11 +257,11 @@ void remy_b200_shutdown(void)
   g_device = -1;
 }
 
-int remy_b200_batch_create(const RemyFlatTree *tree,
-                           const RemyLeafOverride *cands, uint32_t n_cands,
-                           const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
-                           uint32_t sender_stride, int want_senders, int want_use_counts,
-                           RemyBatch **out_batch)
+static int create_impl(const RemyFlatTree *tree,
+                       const RemyLeafOverride *cands, uint32_t n_cands,
+                       const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                       uint32_t sender_stride, int want_senders, int want_use_counts, int trace,
+                       RemyBatch **out_batch)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!out_batch) return fail(REMY_EINVAL, "out_batch is NULL");
@@ -270,14 +278,17 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   RemyBatch *b = guard.get();
   b->n_cands = n_cands; b->n_cfgs = n_cfgs; b->n_sims = n_cands * n_cfgs;
   b->has_cands = cands != nullptr;
-  b->want_senders = want_senders != 0; b->want_counts = want_use_counts != 0;
+  b->want_senders = want_senders != 0; b->want_counts = want_use_counts != 0 || trace != 0;
   b->sender_stride = sender_stride;
+  b->trace = trace;
 
   /* ---- tree -> device layout (validated so the kernel cannot walk off the arrays) ---- */
   PreparedTree pt;
   const std::string terr = prepare_tree(tree, pt);
   if (!terr.empty()) return fail(REMY_EINVAL, terr);
   b->n_nodes = tree->n_nodes; b->n_leaves = tree->n_leaves; b->axes_mask = pt.axes_mask; b->tree_bytes = pt.bytes();
+  b->trace_words = 1u + (uint32_t)__builtin_popcount(pt.axes_mask);
+  if (trace) CU(b->out_lookups.alloc(b->n_sims));
   if (cands)
     for (uint32_t c = 0; c < n_cands; c++)
       if (cands[c].leaf_index != REMY_NO_OVERRIDE && cands[c].leaf_index >= tree->n_leaves)
@@ -347,6 +358,15 @@ int remy_b200_batch_create(const RemyFlatTree *tree,
   CU(cudaStreamSynchronize(g_stream));
   *out_batch = guard.release();
   return 0;
+}
+
+int remy_b200_batch_create(const RemyFlatTree *tree,
+                           const RemyLeafOverride *cands, uint32_t n_cands,
+                           const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                           uint32_t sender_stride, int want_senders, int want_use_counts,
+                           RemyBatch **out_batch)
+{
+  return create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, want_senders, want_use_counts, 0, out_batch);
 }
 
 int remy_b200_batch_run(RemyBatch *b, float *kernel_ms)
@@ -449,6 +469,84 @@ int remy_b200_score_batch(const RemyFlatTree *tree,
   rc = remy_b200_batch_run(b, nullptr);
   if (!rc) rc = remy_b200_batch_fetch(b, out_sims, out_senders, out_use_counts);
   remy_b200_batch_destroy(b);
+  return rc;
+}
+
+/* ---- trace == true scoring ------------------------------------------------------------ */
+int remy_b200_score_trace(const RemyFlatTree *tree,
+                          const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                          uint32_t sender_stride,
+                          RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
+                          RemyTraceSink sink, void *user)
+{
+  if (!out_sims && n_cfgs) return fail(REMY_EINVAL, "out_sims is NULL");
+  if (!sink) return fail(REMY_EINVAL, "sink is NULL");
+  /* 1. counting run: scores, use counts, and the number of lookups of every simulation */
+  RemyBatch *b = nullptr;
+  int rc = create_impl(tree, nullptr, 1, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, 1, 1, &b);
+  if (rc) return rc;
+  std::vector<uint64_t> lookups(n_cfgs);
+  uint32_t words = b->trace_words;
+  rc = remy_b200_batch_run(b, nullptr);
+  if (!rc) rc = remy_b200_batch_fetch(b, out_sims, out_senders, out_use_counts);
+  if (!rc && n_cfgs) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaError_t e = cudaMemcpy(lookups.data(), b->out_lookups.p, n_cfgs * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(REMY_ECUDA, std::string("cudaMemcpy(lookups): ") + cudaGetErrorString(e));
+  }
+  remy_b200_batch_destroy(b);
+  if (rc) return rc;
+  for (uint32_t k = 0; k < n_cfgs; k++)
+    if (out_sims[k].error) return 0; /* a failed simulation has no defined trace (the reference would have exited) */
+
+  /* 2. writing runs over consecutive groups of configs whose log fits the budget */
+  size_t free_b = 0, total_b = 0;
+  { std::lock_guard<std::mutex> lk(g_mu); CU(cudaSetDevice(g_device)); CU(cudaMemGetInfo(&free_b, &total_b)); }
+  uint64_t budget = std::min<uint64_t>(free_b / 3, (uint64_t)32 << 30);
+  if (const char *e = getenv("REMY_B200_TRACE_LOG_BYTES")) { const long long v = atoll(e); if (v > 0) budget = (uint64_t)v; }
+  const uint64_t rec_bytes = (uint64_t)words * sizeof(uint64_t);
+  const size_t stage_bytes = (size_t)64 << 20;
+  uint64_t *stage = nullptr;
+  { std::lock_guard<std::mutex> lk(g_mu); CU(cudaMallocHost(&stage, stage_bytes)); }
+  const uint64_t stage_recs = stage_bytes / rec_bytes;
+  uint32_t g0 = 0;
+  while (g0 < n_cfgs && !rc) {
+    uint32_t g1 = g0; uint64_t recs = 0;
+    std::vector<uint64_t> offs;
+    while (g1 < n_cfgs && (g1 == g0 || (recs + lookups[g1]) * rec_bytes <= budget)) { offs.push_back(recs); recs += lookups[g1]; g1++; }
+    if (recs * rec_bytes > budget && recs * rec_bytes > ((uint64_t)64 << 30)) { rc = fail(REMY_ENOMEM, "trace of one simulation exceeds the log budget"); break; }
+    RemyBatch *g = nullptr;
+    rc = create_impl(tree, nullptr, 1, cfgs + g0, seeds + g0, g1 - g0, sender_stride, 0, 1, 2, &g);
+    if (rc) break;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      cudaError_t e = g->trace_log.alloc(std::max<uint64_t>(recs, 1) * words);
+      if (e == cudaSuccess) e = g->trace_off.alloc(g1 - g0);
+      if (e == cudaSuccess) e = cudaMemcpy(g->trace_off.p, offs.data(), offs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { cudaGetLastError(); rc = fail(REMY_ENOMEM, std::string("trace log allocation: ") + cudaGetErrorString(e)); }
+    }
+    if (!rc) rc = remy_b200_batch_run(g, nullptr);
+    if (!rc) {
+      std::lock_guard<std::mutex> lk(g_mu);
+      cudaError_t e = cudaStreamSynchronize(g_stream);
+      /* hand the records to the sink in config order, through a pinned staging buffer */
+      for (uint32_t k = g0; k < g1 && e == cudaSuccess && !rc; k++) {
+        uint64_t done = 0;
+        const uint64_t n = lookups[k], base = offs[k - g0];
+        do { /* (a config without lookups still gets one empty call) */
+          const uint64_t m = std::min<uint64_t>(n - done, stage_recs);
+          if (m) e = cudaMemcpy(stage, g->trace_log.p + (base + done) * words, m * rec_bytes, cudaMemcpyDeviceToHost);
+          if (e != cudaSuccess) break;
+          if (sink(user, k, stage, m, words)) rc = fail(REMY_EINVAL, "trace sink asked to stop");
+          done += m;
+        } while (done < n && !rc);
+      }
+      if (e != cudaSuccess) rc = fail(REMY_ECUDA, std::string("trace copy: ") + cudaGetErrorString(e));
+    }
+    remy_b200_batch_destroy(g);
+    g0 = g1;
+  }
+  { std::lock_guard<std::mutex> lk(g_mu); cudaFreeHost(stage); }
   return rc;
 }
 

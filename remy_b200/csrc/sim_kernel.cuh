@@ -84,6 +84,12 @@ struct KernelArgs {
   RemySimResult *out_sims;                 /* [n_sims] */
   RemySenderResult *out_senders; uint32_t sender_stride; /* optional */
   uint32_t *out_use_counts;                /* [n_cands][n_leaves], optional */
+  /* trace == true (TRACE kernels only): one record per WhiskerTree::use_whisker call, in the
+   * reference's call order: { leaf, bits of Memory::field(a) for every axis a in axes_mask,
+   * ascending }.  Simulation `sim` writes its records from record index trace_off[sim]; with
+   * trace_log == nullptr the calls are only counted (out_lookups[sim]) so that the host can lay
+   * the log out exactly. */
+  uint64_t *trace_log; const uint64_t *trace_off; uint64_t *out_lookups; uint32_t trace_words;
 };
 
 /* Non-binding request to bring the line holding p towards the SM: used where an address is
@@ -264,7 +270,7 @@ __device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int
 }
 
 /* ------------------------------------------------------------- the sim ---- */
-template <bool COUNT>
+template <bool COUNT, bool TRACE = false>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         double *inc_buf, double *hot_send, uint32_t HS, /* per-tick arrays, element i at [i * HS] */
                         double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
@@ -292,6 +298,22 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   /* candidate override (WhiskerTree::replace, src/whiskertree.cc:137-157) */
   uint32_t ov_leaf = REMY_NO_OVERRIDE;
   if (A.cands) ov_leaf = A.cands[cand].leaf_index;
+
+  /* MemoryRange::track (src/memoryrange.cc:60-66) of the leaf a lookup returned */
+  uint64_t nrec = 0;
+  const uint64_t trace_base = (TRACE && A.trace_off) ? A.trace_off[sim] : 0;
+  auto track = [&](uint32_t leaf, const double *mem) {
+    if (TRACE) {
+      if (A.trace_log) {
+        uint64_t *r = A.trace_log + (trace_base + nrec) * A.trace_words;
+        r[0] = leaf;
+        uint32_t k = 1;
+#pragma unroll
+        for (int a = 0; a < NAX; a++) if (A.axes_mask & (1u << a)) r[k++] = (uint64_t)__double_as_longlong(mem[a]);
+      }
+      nrec++;
+    }
+  };
 
   uint32_t prng = A.seeds[cfg_i] % LCG_M; /* bits/random.tcc:116-126 */
   if (prng == 0) prng = 1;
@@ -398,6 +420,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
               const uint32_t leaf = find_leaf(T, c.mem, err);
               if (err) break;
               if (COUNT) cnt[leaf]++;
+              track(leaf, c.mem);
               DevLeaf w = T.leaves[leaf];
               if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
               c.window = whisker_window(0, w.window_multiple, w.window_increment);
@@ -440,6 +463,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     /* the sender acked in this tick usually transmits in this tick: its send state is handed
      * over in registers instead of being re-read from HBM */
     uint32_t ak_s = 0xFFFFFFFFu, ak_seq = 0; int32_t ak_lim = 0; double ak_isend = 0;
+    uint32_t acked = 0; /* senders whose mailbox was read in this tick */
     if (dcons != ddeliv) {
       sends_dirty = true;
       uint32_t done = 0;
@@ -504,6 +528,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       }
       dcons = ddeliv;
       if (err) break;
+      acked = done;
     }
 
     /* Rat::send's lookup when the window is 0 (rat-templates.cc:13-18): the
@@ -512,6 +537,29 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     if (COUNT) {
       uint32_t zm = zero_mask & on_mask;
       while (zm) { const uint32_t s = __ffs(zm) - 1; zm &= zm - 1; cnt[cold[s].leaf]++; }
+    }
+    /* trace: the lookups of run_senders happen sender by sender in the shuffled order
+     * (sendergang.cc:83-86 -> TimeSwitchedSender::tick, :190-205): the ack's lookup, then
+     * Rat::send's window-0 lookup, both on the Memory the ack left behind.  The order is
+     * observable (the running medians are order dependent), so the permutation is built
+     * whenever two senders looked something up in this tick. */
+    if (TRACE) {
+      const uint32_t zm = zero_mask & on_mask;
+      uint32_t lk = acked | zm;
+      if (lk) {
+        uint8_t perm[REMY_MAX_SENDERS];
+        const bool ordered = (lk & (lk - 1)) != 0;
+        if (ordered) shuffle_materialise(prng_before_shuffle, n, perm);
+        for (uint32_t i = 0; lk; i++) {
+          uint32_t s;
+          if (ordered) { s = perm[i]; if (!((lk >> s) & 1u)) continue; }
+          else s = __ffs(lk) - 1;
+          lk &= ~(1u << s);
+          const SenderCold c = cold[s];
+          if ((acked >> s) & 1u) track(c.leaf, c.mem);
+          if ((zm >> s) & 1u) track(c.leaf, c.mem);
+        }
+      }
     }
 
     /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34) ----
@@ -657,6 +705,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   res.prng_state = prng;
   res.error = err;
   A.out_sims[sim] = res;
+  if (TRACE && A.out_lookups) A.out_lookups[sim] = nrec;
   if (COUNT && A.out_use_counts && !(err & (REMY_ERR_LINK_OVERFLOW | REMY_ERR_DELAY_OVERFLOW))) {
     /* (an overflowed simulation is re-run by the host with larger rings) */
     for (uint32_t l = 0; l < A.n_leaves; l++) {
@@ -670,7 +719,7 @@ constexpr int SIM_BLOCK = 128;
 
 #ifndef REMY_HOST_EMU
 
-template <bool COUNT>
+template <bool COUNT, bool TRACE = false>
 __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -708,7 +757,7 @@ __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
+    run_sim<COUNT, TRACE>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
   }
 }
 

@@ -95,6 +95,27 @@ unsigned int RatBreeder::next_seed()
   return _seed_state;
 }
 
+void RatBreeder::apply_best_split(WhiskerTree &tree, unsigned int generation)
+{ /* src/breeder.cc:15-41 */
+  const Evaluator<WhiskerTree> eval(_options.config_range, next_seed());
+  auto outcome(eval.score(tree, true));
+  while (1) {
+    const Whisker *my_action = outcome.used_actions.most_used(generation);
+    if (!my_action) throw std::runtime_error("apply_best_split: no whisker was used (reference assert, breeder.cc:25)");
+    WhiskerTree bisected_action(*my_action, true);
+    if (bisected_action.num_children() == 1) {
+      printf("Got unbisectable whisker! %s\n", my_action->str().c_str());
+      Whisker mutable_action(*my_action);
+      mutable_action.promote(generation + 1);
+      if (!outcome.used_actions.replace(mutable_action)) throw std::runtime_error("apply_best_split: replace failed (reference assert, breeder.cc:33)");
+      continue;
+    }
+    printf("Bisecting === %s === into === %s ===\n", my_action->str().c_str(), bisected_action.str().c_str());
+    if (!tree.replace(*my_action, bisected_action)) throw std::runtime_error("apply_best_split: replace failed (reference assert, breeder.cc:38)");
+    break;
+  }
+}
+
 Evaluator<WhiskerTree>::Outcome RatBreeder::improve(WhiskerTree &whiskers)
 { /* src/ratbreeder.cc:7-72 */
   WhiskerTree input_whiskertree(whiskers);
@@ -119,7 +140,8 @@ Evaluator<WhiskerTree>::Outcome RatBreeder::improve(WhiskerTree &whiskers)
     whisker_to_improve.demote(generation + 1);
     if (!whiskers.replace(whisker_to_improve)) throw std::runtime_error("RatBreeder: replace failed (reference assert, ratbreeder.cc:55)");
   }
-  /* (apply_best_split is not mirrored, see breeder.hh) */
+  /* Split most used whisker */
+  apply_best_split(whiskers, generation);
   const Evaluator<WhiskerTree> eval2(_options.config_range, next_seed());
   const auto new_score = eval2.score(whiskers, false, 10);
   const auto old_score = eval2.score(input_whiskertree, false, 10);

@@ -7,11 +7,11 @@
  * batch call (Evaluator::score_candidates) instead of one std::async thread per candidate
  * (src/breeder.cc:57-69).
  *
- * Not mirrored: Breeder::apply_best_split (src/breeder.cc:15-41) — it needs trace=true scoring
- * with Boost's P^2 running medians per leaf, whose values depend on the order in which ONE
- * thread visits all configs; that is outside this round.  RatBreeder::improve
- * therefore optimises the actions of the existing whiskers and does the final regression check,
- * but does not grow the tree.
+ * Breeder::apply_best_split (src/breeder.cc:15-41) scores the tree with trace == true
+ * (remy_b200_score_trace feeds every leaf's P^2 running medians in the reference's order) and
+ * bisects the most used whisker at those medians.  In the fork the function starts with a
+ * stray `assert(false)` ("FIXME: Just for debugging", src/breeder.cc:18-19), so the fork's own
+ * `remy` aborts here; this mirror implements what the code below that line does.
  */
 #ifndef REMY_HOST_BREEDER_HH
 #define REMY_HOST_BREEDER_HH
@@ -63,6 +63,7 @@ class RatBreeder {
 public:
   RatBreeder(const BreederOptions &options, const WhiskerImproverOptions &whisker_options, unsigned int seed = 0);
   Evaluator<WhiskerTree>::Outcome improve(WhiskerTree &whiskers);
+  void apply_best_split(WhiskerTree &whiskers, unsigned int generation);  /* Breeder<T>::apply_best_split */
   size_t candidates_scored = 0, batches = 0;
 };
 

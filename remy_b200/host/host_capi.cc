@@ -174,7 +174,7 @@ long remy_host_improve_whisker(void *h, const void *range_bytes, size_t range_si
     return calls;)
 }
 
-/* RatBreeder::improve (without apply_best_split); the tree behind `h` is updated in place */
+/* RatBreeder::improve; the tree behind `h` is updated in place */
 int remy_host_ratbreeder_improve(void *h, const void *range_bytes, size_t range_size, unsigned int seed, double *score, double *stats)
 {
   GUARD(
@@ -184,6 +184,97 @@ int remy_host_ratbreeder_improve(void *h, const void *range_bytes, size_t range_
     const auto outcome = b.improve(t);
     *score = outcome.score;
     if (stats) { stats[0] = (double)b.candidates_scored; stats[1] = (double)b.batches; }
+    return 0;)
+}
+
+/* ---- trace == true ---- */
+
+/* P2Median fed with `n` samples — no GPU needed */
+double remy_host_p2_median(const double *samples, size_t n)
+{
+  P2Median acc;
+  for (size_t i = 0; i < n; i++) acc(samples[i]);
+  return acc.median();
+}
+
+/* MemoryRange::track of leaf `leaf_index` with `n` Memory values (6 doubles each) — no GPU needed */
+int remy_host_track(void *h, uint32_t leaf_index, const double *mem, size_t n)
+{
+  GUARD(
+    std::vector<Whisker *> lv; ((WhiskerTree *)h)->leaves(lv);
+    if (leaf_index >= lv.size()) throw std::runtime_error("leaf index out of range");
+    Memory m;
+    for (size_t i = 0; i < n; i++) { for (unsigned a = 0; a < Memory::datasize; a++) m.f[a] = mem[i * Memory::datasize + a]; lv[leaf_index]->domain().track(m); }
+    return 0;)
+}
+
+/* median(_acc[axis]) of every leaf: out[leaf * 6 + axis] — no GPU needed */
+int remy_host_medians(void *h, double *out, uint32_t n_leaves)
+{
+  GUARD(
+    std::vector<const Whisker *> lv; ((WhiskerTree *)h)->leaves(lv);
+    for (size_t l = 0; l < lv.size() && l < n_leaves; l++)
+      for (unsigned a = 0; a < Memory::datasize; a++) out[l * Memory::datasize + a] = lv[l]->domain()._acc[a].median();
+    return 0;)
+}
+
+/* set the use counts of the leaves (what a scoring run leaves behind) — no GPU needed */
+int remy_host_set_counts(void *h, const uint32_t *counts, uint32_t n_leaves)
+{
+  GUARD(
+    std::vector<Whisker *> lv; ((WhiskerTree *)h)->leaves(lv);
+    for (size_t l = 0; l < lv.size() && l < n_leaves; l++) lv[l]->_domain._count = counts[l];
+    return 0;)
+}
+
+/* The loop of Breeder::apply_best_split (src/breeder.cc:23-40) on a tree whose leaves already carry
+ * use counts and running medians — no GPU needed */
+int remy_host_split_most_used(void *h, unsigned int generation)
+{
+  GUARD(
+    WhiskerTree &tree = *(WhiskerTree *)h;
+    WhiskerTree used_actions(tree);
+    while (1) {
+      const Whisker *my_action = used_actions.most_used(generation);
+      if (!my_action) throw std::runtime_error("no whisker was used");
+      WhiskerTree bisected_action(*my_action, true);
+      if (bisected_action.num_children() == 1) {
+        Whisker mutable_action(*my_action);
+        mutable_action.promote(generation + 1);
+        used_actions.replace(mutable_action);
+        continue;
+      }
+      tree.replace(*my_action, bisected_action);
+      break;
+    }
+    return 0;)
+}
+
+/* Evaluator<WhiskerTree>::score(tree, seed, configs, trace = true, ticks) over explicit NetConfigs — needs a GPU.
+ * The tree behind `h` keeps the use counts and the running medians. */
+int remy_host_score_trace(void *h, const RemyNetConfig *cfgs, uint32_t n_cfgs, unsigned int prng_seed, double *score)
+{
+  GUARD(
+    WhiskerTree &t = *(WhiskerTree *)h;
+    std::vector<NetConfig> configs;
+    for (uint32_t k = 0; k < n_cfgs; k++) {
+      NetConfig c; c.mean_on_duration = cfgs[k].mean_on_duration; c.mean_off_duration = cfgs[k].mean_off_duration;
+      c.num_senders = cfgs[k].num_senders; c.link_ppt = cfgs[k].link_ppt; c.delay = cfgs[k].delay;
+      c.buffer_size = cfgs[k].buffer_size; c.stochastic_loss_rate = cfgs[k].stochastic_loss_rate;
+      configs.push_back(c);
+    }
+    const auto out = Evaluator<WhiskerTree>::score(t, prng_seed, configs, true, n_cfgs ? (unsigned int)cfgs[0].simulation_ticks : 0);
+    *score = out.score;
+    return 0;)
+}
+
+/* Breeder::apply_best_split through RatBreeder — needs a GPU */
+int remy_host_apply_best_split(void *h, const void *range_bytes, size_t range_size, unsigned int seed, unsigned int generation)
+{
+  GUARD(
+    BreederOptions o; o.config_range = ConfigRange::parse(range_bytes, range_size);
+    RatBreeder b(o, WhiskerImproverOptions(), seed);
+    b.apply_best_split(*(WhiskerTree *)h, generation);
     return 0;)
 }
 

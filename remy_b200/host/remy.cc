@@ -136,6 +136,62 @@ std::string Memory::str(unsigned int num) const
 }
 
 /* ------------------------------------------------------------ MemoryRange -- */
+P2Median::P2Median() : _cnt(0)
+{ /* p_square_quantile_impl's constructor for p = 0.5 */
+  const double p = 0.5;
+  for (int i = 0; i < 5; i++) { _h[i] = 0; _n[i] = i + 1.; }
+  _d[0] = 1.; _d[1] = 1. + 2. * p; _d[2] = 1. + 4. * p; _d[3] = 3. + 2. * p; _d[4] = 5.;
+}
+void P2Median::operator()(double x)
+{
+  static const double incr[5] = { 0., 0.5 / 2., 0.5, (1. + 0.5) / 2., 1. };
+  if (++_cnt <= 5) {
+    _h[_cnt - 1] = x;
+    if (_cnt == 5) std::sort(_h, _h + 5);
+    return;
+  }
+  size_t k;
+  if (x < _h[0]) { _h[0] = x; k = 1; }
+  else if (_h[4] <= x) { _h[4] = x; k = 4; }
+  else k = (size_t)(std::upper_bound(_h, _h + 5, x) - _h);
+  for (size_t i = k; i < 5; i++) ++_n[i];
+  for (size_t i = 0; i < 5; i++) _d[i] += incr[i];
+  for (size_t i = 1; i <= 3; i++) {
+    const double d = _d[i] - _n[i], dp = _n[i + 1] - _n[i], dm = _n[i - 1] - _n[i];
+    const double hp = (_h[i + 1] - _h[i]) / dp, hm = (_h[i - 1] - _h[i]) / dm;
+    if ((d >= 1. && dp > 1.) || (d <= -1. && dm < -1.)) {
+      const short sign_d = static_cast<short>(d / std::abs(d));
+      const double h = _h[i] + sign_d / (dp - dm) * ((sign_d - dm) * hp + (dp - sign_d) * hm);
+      if (_h[i - 1] < h && h < _h[i + 1]) _h[i] = h;
+      else { if (d > 0) _h[i] += hp; if (d < 0) _h[i] -= hm; }
+      _n[i] += sign_d;
+    }
+  }
+}
+void MemoryRange::track(const Memory &q) const
+{ for (int i : _active_axis) _acc[i](q.field(i)); }
+std::vector<MemoryRange> MemoryRange::bisect() const
+{ /* src/memoryrange.cc:8-41 */
+  std::vector<MemoryRange> ret { *this };
+  for (int i : _active_axis) {
+    std::vector<MemoryRange> doubled;
+    for (const auto &x : ret) {
+      Memory ersatz_lower(x._lower), ersatz_upper(x._upper);
+      ersatz_lower.mutable_field(i) = ersatz_upper.mutable_field(i) = _acc[i].median();
+      if (x._lower == ersatz_upper) /* try range midpoint instead */
+        ersatz_lower.mutable_field(i) = ersatz_upper.mutable_field(i) = (x._lower.field(i) + x._upper.field(i)) / 2;
+      if (x._lower == ersatz_upper) {
+        if (ersatz_lower == x._upper || !(x._lower == ersatz_lower)) throw std::runtime_error("MemoryRange::bisect: degenerate range (reference assert, memoryrange.cc:26-27)");
+        doubled.push_back(x); /* cannot double on this axis */
+      } else {
+        doubled.emplace_back(x._lower, ersatz_upper, x._active_axis);
+        doubled.emplace_back(ersatz_lower, x._upper, x._active_axis);
+      }
+    }
+    ret = doubled;
+  }
+  return ret;
+}
 bool MemoryRange::contains(const Memory &q) const
 { /* src/memoryrange.cc:52-58 */
   for (int i : _active_axis)
@@ -233,6 +289,12 @@ void Whisker::round()
   _window_multiple = (1.0 / 10000.0) * int(10000 * _window_multiple);
   _intersend = (1.0 / 10000.0) * int(10000 * _intersend);
 }
+std::vector<Whisker> Whisker::bisect() const
+{ /* Action::bisect<Whisker>, src/action.hh:25-33 */
+  std::vector<Whisker> ret;
+  for (const auto &x : _domain.bisect()) { Whisker new_action(*this); new_action._domain = x; ret.push_back(new_action); }
+  return ret;
+}
 std::vector<Whisker> Whisker::next_generation(bool oi, bool om, bool os) const
 { /* src/whisker.cc:46-81 (without its printf) */
   std::vector<Whisker> ret;
@@ -285,12 +347,31 @@ const Whisker *WhiskerTree::whisker(const Memory &m) const
   for (const auto &x : _children) { const Whisker *r = x.whisker(m); if (r) return r; }
   throw std::runtime_error("WhiskerTree: no child contains the query (reference: assert(false), whiskertree.cc:80)");
 }
-const Whisker &WhiskerTree::use_whisker(const Memory &m, bool) const
+const Whisker &WhiskerTree::use_whisker(const Memory &m, bool track) const
 { /* src/whiskertree.cc:42-60 */
   const Whisker *ret = whisker(m);
   if (!ret) throw std::runtime_error("ERROR: No whisker found for " + m.str());
   ret->domain().use();
+  if (track) ret->domain().track(m);
   return *ret;
+}
+WhiskerTree::WhiskerTree(const Whisker &whisker, bool bisect) : _domain(whisker.domain())
+{ /* src/whiskertree.cc:17-30 */
+  if (!bisect) _leaf.push_back(whisker);
+  else for (const auto &x : whisker.bisect()) _children.push_back(WhiskerTree(x, false));
+}
+bool WhiskerTree::replace(const Whisker &src, const WhiskerTree &dst)
+{ /* src/whiskertree.cc:159-180 */
+  if (!_domain.contains(src.domain().range_median())) return false;
+  if (is_leaf()) {
+    if (!(src.domain() == _leaf.front().domain())) throw std::runtime_error("WhiskerTree::replace: domain mismatch (reference assert)");
+    const std::string extra = _extra;
+    *this = dst; /* convert from leaf to interior node */
+    _extra = extra;
+    return true;
+  }
+  for (auto &x : _children) if (x.replace(src, dst)) return true;
+  throw std::runtime_error("WhiskerTree::replace: no child took the whisker (reference assert)");
 }
 void WhiskerTree::reset_counts()
 { if (is_leaf()) _leaf.front().domain().reset_count(); else for (auto &x : _children) x.reset_counts(); }
@@ -462,8 +543,30 @@ static void check_sim(const RemySimResult &r)
   if (r.error) throw std::runtime_error("simulation failed with error word " + std::to_string(r.error));
 }
 
+namespace {
+/* What remy_b200_score_trace's records are fed into: MemoryRange::track of the leaf each lookup
+ * returned (src/whiskertree.cc:55-57), in the order the device reports them (config by config,
+ * and within a config in the reference's call order). */
+struct TrackSink {
+  std::vector<Whisker *> leaves;
+  std::vector<int> axes; /* axis of record word 1, 2, ... */
+  static int feed(void *user, uint32_t, const uint64_t *rec, uint64_t n, uint32_t words)
+  {
+    TrackSink *t = static_cast<TrackSink *>(user);
+    if (words != t->axes.size() + 1) return 1;
+    Memory m;
+    for (uint64_t i = 0; i < n; i++, rec += words) {
+      if (rec[0] >= t->leaves.size()) return 1;
+      for (size_t k = 0; k < t->axes.size(); k++) memcpy(&m.mutable_field(t->axes[k]), &rec[1 + k], sizeof(double));
+      t->leaves[rec[0]]->domain().track(m);
+    }
+    return 0;
+  }
+};
+} // namespace
+
 Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_whiskers, unsigned int prng_seed,
-    const std::vector<NetConfig> &configs, bool /*trace*/, unsigned int ticks_to_run)
+    const std::vector<NetConfig> &configs, bool trace, unsigned int ticks_to_run)
 {
   const FlatTree ft = flatten(run_whiskers);
   const RemyFlatTree tree = ft.c();
@@ -474,7 +577,16 @@ Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_w
   std::vector<RemySimResult> sims(cfgs.size());
   std::vector<RemySenderResult> snd(cfgs.size() * (size_t)stride);
   std::vector<uint32_t> counts(ft.leaves.size());
-  if (remy_b200_score_batch(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
+  if (trace) { /* Rat(run_whiskers, trace) (src/evaluator.cc:93): every lookup also feeds the leaf's running medians */
+    TrackSink sink;
+    run_whiskers.leaves(sink.leaves);
+    uint32_t mask = 0;
+    for (const auto &nd : ft.nodes) mask |= nd.axis_mask;
+    for (int a = 0; a < REMY_NUM_AXES; a++) if (mask & (1u << a)) sink.axes.push_back(a);
+    if (remy_b200_score_trace(&tree, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
+                              sims.data(), snd.data(), counts.data(), TrackSink::feed, &sink))
+      throw std::runtime_error(std::string("remy_b200_score_trace: ") + remy_b200_last_error());
+  } else if (remy_b200_score_batch(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
                             sims.data(), snd.data(), counts.data()))
     throw std::runtime_error(std::string("remy_b200_score_batch: ") + remy_b200_last_error());
   Outcome out;

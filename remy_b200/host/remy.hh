@@ -10,7 +10,9 @@
  *   Whisker                       src/whisker.hh:11-67, src/whisker.cc:46-95, src/action.hh:12-105
  *   WhiskerTree                   src/whiskertree.hh:11-47, src/whiskertree.cc
  *   Evaluator<WhiskerTree>        src/evaluator.hh:14-56, src/evaluator.cc:9-38,77-103,196-201
- * Not mirrored (out of scope): trace/track medians, bisect, FinTree.
+ *   trace == true scoring         src/memoryrange.cc:8-41,60-66 (track, bisect), src/action.hh:25-33,
+ *                                 src/whiskertree.cc:17-30,159-180, on remy_b200_score_trace
+ * Not mirrored (out of scope): FinTree.
  */
 #ifndef REMY_HOST_REMY_HH
 #define REMY_HOST_REMY_HH
@@ -81,6 +83,19 @@ public:
 };
 const Memory &MAX_MEMORY();
 
+/* boost::accumulators::accumulator_set<double, stats<tag::median>> (src/memoryrange.hh:24-26):
+ * Boost's tag::median is the P^2 running estimator with p = 0.5 (p_square_quantile_impl), not an
+ * exact median, and its value depends on the order of the samples. */
+class P2Median {
+  double _h[5], _n[5], _d[5];
+  size_t _cnt;
+public:
+  P2Median();
+  void operator()(double sample);
+  double median() const { return _h[2]; }
+  size_t count() const { return _cnt; }
+};
+
 class MemoryRange {
 public:
   Memory _lower, _upper;
@@ -89,8 +104,11 @@ public:
   bool _upper_has[Memory::datasize] = { true, true, true, true, true, true };
   bool _axes_explicit = true;
   mutable unsigned int _count = 0;
+  mutable std::vector<P2Median> _acc = std::vector<P2Median>(Memory::datasize);
   MemoryRange() : _upper(MAX_MEMORY()) {}
   MemoryRange(const Memory &lo, const Memory &hi, std::vector<int> active = { 0, 1, 2, 3 }) : _lower(lo), _upper(hi), _active_axis(active) {}
+  std::vector<MemoryRange> bisect() const;                /* src/memoryrange.cc:8-41 */
+  void track(const Memory &q) const;                      /* src/memoryrange.cc:60-66 */
   bool contains(const Memory &q) const;
   Memory range_median() const;
   void use() const { _count++; }
@@ -130,6 +148,7 @@ public:
   void promote(unsigned int g) { if (g > _generation) _generation = g; }
   void demote(unsigned int g) { _generation = g; }
   std::vector<Whisker> next_generation(bool optimize_window_increment, bool optimize_window_multiple, bool optimize_intersend) const;
+  std::vector<Whisker> bisect() const;                    /* Action::bisect<Whisker>, src/action.hh:25-33 */
   void round();
   std::string str(unsigned int total = 1) const;
   bool operator==(const Whisker &o) const { return _window_increment == o._window_increment && _window_multiple == o._window_multiple && _intersend == o._intersend && _domain == o._domain; }
@@ -147,10 +166,12 @@ public:
   std::vector<Whisker> _leaf;
   std::string _extra;                             /* fields 4-6 (config / optimizer / configvector), kept verbatim */
   WhiskerTree();                                  /* one default whisker over [0, MAX_MEMORY) */
+  WhiskerTree(const Whisker &whisker, bool bisect); /* src/whiskertree.cc:17-30 */
   bool is_leaf() const { return !_leaf.empty(); }
   unsigned int num_children() const { return is_leaf() ? 1 : (unsigned)_children.size(); }
   const Whisker &use_whisker(const Memory &m, bool track) const;      /* exits like the reference on a miss */
   bool replace(const Whisker &w);
+  bool replace(const Whisker &src, const WhiskerTree &dst);           /* leaf -> interior node, src/whiskertree.cc:159-180 */
   const Whisker *most_used(unsigned int max_generation) const;
   void reset_counts();
   void promote(unsigned int generation);

@@ -3,7 +3,8 @@
  * arguments (if= of= opt= cf=), same stdout, same checkpoint files (`<of>.<run>` = the WhiskerTree
  * with its config, optimizer and configvector sub-messages).  cf= accepts ConfigRange and
  * ConfigRangeUnicorn files (the reference's own remy silently reads 0 ticks from the latter,
- * SURVEY.md Appendix A).  The tree is not split (see breeder.hh), so runs refine whisker actions.
+ * SURVEY.md Appendix A).  Every run optimises the whisker actions and then bisects the most used
+ * whisker (RatBreeder::improve incl. apply_best_split, see breeder.hh).
  * Extensions: runs=N (stop after N improve() rounds; default: forever, like the reference),
  *             seed=N (default time ^ pid), dev=N.
  */

@@ -39,11 +39,23 @@ class HostLib:
         L.remy_host_improve_whisker.restype = C.c_long
         L.remy_host_improve_whisker.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint32, _V]
         L.remy_host_ratbreeder_improve.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_double), _V]
+        L.remy_host_p2_median.restype = C.c_double
+        L.remy_host_p2_median.argtypes = [_V, C.c_size_t]
+        L.remy_host_track.argtypes = [_V, C.c_uint32, _V, C.c_size_t]
+        L.remy_host_medians.argtypes = [_V, _V, C.c_uint32]
+        L.remy_host_set_counts.argtypes = [_V, _V, C.c_uint32]
+        L.remy_host_split_most_used.argtypes = [_V, C.c_uint]
+        L.remy_host_score_trace.argtypes = [_V, _V, C.c_uint32, C.c_uint, C.POINTER(C.c_double)]
+        L.remy_host_apply_best_split.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint]
         L.remy_host_score_next_generation.restype = C.c_long
         L.remy_host_score_next_generation.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.c_uint32, _V, C.c_uint32]
 
     def err(self):
         return self.lib.remy_host_last_error().decode()
+
+    def p2_median(self, samples):
+        a = np.ascontiguousarray(samples, dtype=np.float64)
+        return self.lib.remy_host_p2_median(a.ctypes.data, len(a))
 
     def _check(self, ok):
         if not ok:
@@ -143,6 +155,33 @@ class HostTree:
         n = self.host.lib.remy_host_improve_whisker(self.h, range_bytes, len(range_bytes), prng_seed, leaf, out.ctypes.data)
         self.host._check(n >= 0)
         return int(n), float(out[0]), (int(out[1]), float(out[2]), float(out[3])), int(out[4]), int(out[5])
+
+    def track(self, leaf, mem):
+        """MemoryRange::track of leaf `leaf` with mem[n, 6]."""
+        a = np.ascontiguousarray(mem, dtype=np.float64)
+        self.host._check(self.host.lib.remy_host_track(self.h, leaf, a.ctypes.data, len(a)) == 0)
+
+    def medians(self, n_leaves):
+        out = np.zeros((n_leaves, abi.NUM_AXES))
+        self.host._check(self.host.lib.remy_host_medians(self.h, out.ctypes.data, n_leaves) == 0)
+        return out
+
+    def set_counts(self, counts):
+        a = np.ascontiguousarray(counts, dtype=np.uint32)
+        self.host._check(self.host.lib.remy_host_set_counts(self.h, a.ctypes.data, len(a)) == 0)
+
+    def split_most_used(self, generation=0):
+        self.host._check(self.host.lib.remy_host_split_most_used(self.h, generation) == 0)
+
+    def score_trace(self, cfgs, prng_seed):
+        """Evaluator::score(tree, seed, configs, trace=true, ticks) (needs a GPU)."""
+        cfgs = np.ascontiguousarray(cfgs, dtype=abi.net_config_dtype)
+        score = C.c_double(0)
+        self.host._check(self.host.lib.remy_host_score_trace(self.h, cfgs.ctypes.data, len(cfgs), prng_seed, C.byref(score)) == 0)
+        return score.value
+
+    def apply_best_split(self, range_bytes, seed, generation=0):
+        self.host._check(self.host.lib.remy_host_apply_best_split(self.h, range_bytes, len(range_bytes), seed, generation) == 0)
 
     def ratbreeder_improve(self, range_bytes, seed):
         score = C.c_double(0)

@@ -57,3 +57,55 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
   }
   return 0;
 }
+
+/* trace == true on the CPU build of the kernel: per config k, out_lookups[k] records of
+ * trace_words = 1 + popcount(axes) words each, written back to back into `log` (capacity
+ * cap_records records; returns REMY_ENOMEM if it does not fit).  Two runs per simulation, like
+ * the library: a counting run, then the run that writes. */
+extern "C" int remy_emu_trace(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                              RemySimResult *out_sims, uint32_t *out_use_counts,
+                              uint64_t *log, uint64_t cap_records, uint64_t *out_lookups, uint32_t *out_words)
+{
+  PreparedTree pt;
+  if (!prepare_tree(tree, pt).empty()) return REMY_EINVAL;
+  BatchPlan plan = plan_batch(cfgs, n_cfgs, 1);
+  std::vector<SenderCold> cold(plan.n_max);
+  std::vector<SendState> sendst(plan.n_max);
+  std::vector<DelayEnt> dring(plan.delay_cap);
+  std::vector<uint32_t> cnt(tree->n_leaves);
+  std::vector<double> hot(INC_BUF + plan.n_max), share(plan.n_max), nsw(plan.n_max);
+  std::vector<uint64_t> offs(n_cfgs, 0);
+  std::vector<uint32_t> scratch_counts(tree->n_leaves);
+  if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * tree->n_leaves);
+  const uint32_t words = 1 + (uint32_t)__builtin_popcount(pt.axes_mask);
+  if (out_words) *out_words = words;
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < n_cfgs; k++) {
+    for (int phase = 0; phase < 2; phase++) {
+      uint32_t cap = plan.link_cap;
+      for (;;) {
+        std::vector<LinkEnt> lring(cap);
+        KernelArgs A;
+        memset(&A, 0, sizeof A);
+        A.bounds = pt.bounds.data(); A.meta = pt.meta.data(); A.leaves = pt.leaves.data();
+        A.cuts = pt.cuts.data(); A.table = pt.table.data(); A.n_cuts = (uint32_t)pt.cuts.size(); A.n_table = (uint32_t)pt.table.size();
+        A.n_nodes = tree->n_nodes; A.n_leaves = tree->n_leaves; A.axes_mask = pt.axes_mask; A.tree_in_smem = 0;
+        A.cands = nullptr; A.cfgs = cfgs; A.seeds = seeds; A.n_cfgs = n_cfgs;
+        A.n_max = plan.n_max; A.link_cap = cap; A.delay_cap = plan.delay_cap;
+        A.out_sims = out_sims; A.out_senders = nullptr; A.sender_stride = 0;
+        A.out_use_counts = phase == 1 ? out_use_counts : scratch_counts.data();
+        A.trace_log = phase == 1 ? log : nullptr; A.trace_off = offs.data(); A.out_lookups = out_lookups; A.trace_words = words;
+        TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
+        run_sim<true, true>(A, T, k, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        if (!(out_sims[k].error & REMY_ERR_LINK_OVERFLOW) || cap >= (1u << 24)) break;
+        cap *= 16;
+      }
+      if (phase == 0) {
+        offs[k] = total;
+        if (total + out_lookups[k] > cap_records) return REMY_ENOMEM;
+      }
+    }
+    total += out_lookups[k];
+  }
+  return 0;
+}

@@ -42,6 +42,7 @@ static inline int32_t __double2int_rz(double v)
   if (v <= -2147483648.0) return (int32_t)0x80000000;
   return (int32_t)v;
 }
+static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, sizeof r); return r; }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 using std::max;
 using std::min;

@@ -81,9 +81,15 @@ def test_remy_cli_writes_checkpoints(built, device, tmp_path):
     assert msg.SerializeToString() == raw
     assert msg.config.simulation_ticks == 4000 and msg.config.num_senders.high == 6
     assert msg.optimizer.intersend.min_value == 0.25 and msg.optimizer.window_increment.max_value == 256
-    assert len(msg.configvector.config) == 4 and msg.HasField("leaf")
-    leaf = msg.leaf
-    assert 0 <= leaf.window_increment <= 256 and 0 <= leaf.window_multiple <= 1 and 0.25 <= leaf.intersend <= 3
+    assert len(msg.configvector.config) == 4
+    # one run = optimise the single whisker, then bisect it at the running medians of its four signals
+    # (Breeder::apply_best_split) -- unless the careful re-evaluation found a regression and kept the input
+    leaves = [msg.leaf] if msg.HasField("leaf") else [c.leaf for c in msg.children]
+    assert len(leaves) in (1, 16) and ("Bisecting ===" in out.stdout)
+    if len(leaves) == 16:
+        assert all(c.HasField("leaf") and c.domain.upper.rtt_ratio > c.domain.lower.rtt_ratio for c in msg.children)
+    for leaf in leaves:
+        assert 0 <= leaf.window_increment <= 256 and 0 <= leaf.window_multiple <= 1 and 0.25 <= leaf.intersend <= 3
     # the optimiser only ever accepts strict improvements, and the checkpoint feeds straight back into sender-runner
     assert "Regression" not in out.stderr or "Ending search." in out.stderr
     sr = subprocess.run([os.path.join(ROOT, "remy_b200", "host", "sender-runner"), f"if={of}.0", "nsrc=2", "link=1", "rtt=100",
