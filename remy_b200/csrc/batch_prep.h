@@ -81,10 +81,13 @@ inline void build_cell_table(PreparedTree &t, uint32_t node)
   };
   md.table_off = (uint32_t)t.table.size();
   md.cuts_off = (uint32_t)t.cuts.size();
+  bool bisected = t.axes_mask == 0xFu;
   for (int a = 0; a < NAX; a++) {
     md.ncuts[a] = (uint8_t)n_int[a];
+    if ((t.axes_mask & (1u << a)) && n_int[a] != 1) bisected = false;
     t.cuts.insert(t.cuts.end(), cuts[a].begin() + lo_skip[a], cuts[a].begin() + lo_skip[a] + n_int[a]);
   }
+  md.ncuts[7] = bisected ? 1 : 0; /* one interior cut on each of the four default axes: the kernel's fast path */
   t.table.resize(t.table.size() + cells, NO_CELL_CHILD);
   std::vector<int> p(NAX, 0);
   for (size_t cell = 0; cell < cells; cell++) {

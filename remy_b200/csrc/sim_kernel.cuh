@@ -94,6 +94,14 @@ struct KernelArgs {
 
 /* Non-binding request to bring the line holding p towards the SM: used where an address is
  * known ticks before its data is needed (next ring line, the next sender to transmit). */
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+#ifdef REMY_HOST_EMU
+  (void)p;
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 __device__ __forceinline__ void prefetch_line(const void *p)
 {
 #ifdef REMY_HOST_EMU
@@ -233,6 +241,9 @@ __device__ __forceinline__ uint32_t find_leaf(const TreeView &T, const double *m
       /* cell lookup: p_a = #{cuts <= m[a]} per axis, then one table read */
       const double *cp = T.cuts + md.cuts_off;
       uint32_t idx = 0, stride = 1;
+      if (md.ncuts[7] && T.axes_mask == 0xFu) { /* bisected once on each of the four default axes (Whisker::bisect) */
+        idx = (m[0] >= cp[0] ? 1u : 0u) | (m[1] >= cp[1] ? 2u : 0u) | (m[2] >= cp[2] ? 4u : 0u) | (m[3] >= cp[3] ? 8u : 0u);
+      } else
 #pragma unroll
       for (int a = 0; a < NAX; a++) {
         if (T.axes_mask & (1u << a)) {
@@ -320,12 +331,11 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   uint32_t err = 0;
 
   const double duration = cfg.simulation_ticks;
-  const double start_rate = __ddiv_rn(1.0, cfg.mean_off_duration); /* sendergang.cc:18-19 */
-  const double stop_rate = __ddiv_rn(1.0, cfg.mean_on_duration);
+  /* Per-simulation constants that are only needed on rare paths (switches) or once per packet are
+   * re-read from the config array (a broadcast, cache-resident load) instead of living in registers:
+   * the event loop keeps ~60 values live and spills would land in its hottest part. */
+  const RemyNetConfig *cfgp = &A.cfgs[cfg_i];
   const double service = __ddiv_rn(1.0, cfg.link_ppt);            /* link.hh:24 */
-  const double delay = cfg.delay;
-  const double loss_p = cfg.stochastic_loss_rate;
-  const uint32_t limit = cfg.buffer_size;
   const uint32_t lmask = A.link_cap - 1, dmask = A.delay_cap - 1;
 
   /* SenderGang ctor (sendergang.cc:9-26), Rat ctor (rat.cc:8-20) */
@@ -337,7 +347,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0; c.total_delay = 0;
     c.last_send_time = 0; c.intersend = 0;
     c.reserved = 0;
-    const double first_switch = exp_sample(prng, start_rate);
+    const double first_switch = exp_sample(prng, __ddiv_rn(1.0, cfg.mean_off_duration)); /* sendergang.cc:18-19 */
     nsw[s] = first_switch;
     c.packets_sent = 0; c.largest_ack = -1; c.window = 0; c.u_received = 0; c.leaf = 0; c.pad = 0;
     cold[s] = c;
@@ -360,7 +370,6 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   /* ... and so is the entry behind it (valid when dtail - ddeliv >= 2), so that the HBM read of
    * a delay-ring entry is issued a whole service time before its first use */
   double dn_release = 0, dn_sent = 0; uint32_t dn_seq = 0, dn_src = 0;
-  double m_sent = 0; uint32_t m_seq = 0, m_src = 0;
   uint64_t iters = 0;
   /* Sending time is accumulated exactly as the reference does (one rounded addition of
    * dt/k per sender per tick, sendergang.cc:163-173), but the additions are deferred: the
@@ -370,102 +379,239 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   uint32_t ninc = 0, acc_mask = 0;
   auto flush_share = [&]() {
     uint32_t am = acc_mask;
+    /* always INC_BUF additions per sender, from registers: unused slots hold +0.0, and v + 0.0 == v
+     * exactly for the non-negative sums kept here */
+    for (uint32_t k = ninc; k < INC_BUF; k++) inc_buf[k * HS] = 0.0;
+    double inc[INC_BUF];
+#pragma unroll
+    for (uint32_t k = 0; k < INC_BUF; k++) inc[k] = inc_buf[k * HS];
     while (am) {
       const uint32_t s = __ffs(am) - 1; am &= am - 1;
       double v = share[s];
-      for (uint32_t k = 0; k < ninc; k++) v = __dadd_rn(v, inc_buf[k * HS]);
+#pragma unroll
+      for (uint32_t k = 0; k < INC_BUF; k++) v = __dadd_rn(v, inc[k]);
       share[s] = v;
     }
     ninc = 0;
   };
 
-  while (t < duration) {
-    /* ---- next event (network.cc:75-78) ---- */
+  /* One pass of this loop = one reference tick, or two when the tick delivers a packet: the tick
+   * that follows a delivery happens at the same time t (Receiver::next_event_time, receiver.hh:34-37)
+   * and consists of nothing but the shuffle's draws, the ack and the sends it releases, so it is run
+   * in the same pass, right behind the delivery ("fused tick").  Every lane of a warp then reaches
+   * the expensive ack code once per pass instead of once every other pass.  For that the link and
+   * delay phases of a tick come BEFORE the (single) ack/send code in the pass, which is only
+   * equivalent if the tick itself has nothing to send; a tick that may send AND has a departure or
+   * a delivery due is therefore split over two passes (`half`): senders first, link + delay (and
+   * the fused tick) in the next pass. */
+  bool half = false, maybe_sends = false;
+  uint32_t prng_before_shuffle = prng;
+  /* trace: the lookups of run_senders happen sender by sender in the shuffled order
+   * (sendergang.cc:83-86 -> TimeSwitchedSender::tick, :190-205): the ack's lookup, then
+   * Rat::send's window-0 lookup, both on the Memory the ack left behind.  The order is
+   * observable (the running medians are order dependent), so the permutation is built
+   * whenever two senders looked something up in one tick. */
+  auto track_senders = [&](uint32_t acked, uint32_t zm) {
+    uint32_t lk = acked | zm;
+    if (lk) {
+      uint8_t perm[REMY_MAX_SENDERS];
+      const bool ordered = (lk & (lk - 1)) != 0;
+      if (ordered) shuffle_materialise(prng_before_shuffle, n, perm);
+      for (uint32_t i = 0; lk; i++) {
+        uint32_t s;
+        if (ordered) { s = perm[i]; if (!((lk >> s) & 1u)) continue; }
+        else s = __ffs(lk) - 1;
+        lk &= ~(1u << s);
+        const SenderCold c = cold[s];
+        if ((acked >> s) & 1u) track(c.leaf, c.mem);
+        if ((zm >> s) & 1u) track(c.leaf, c.mem);
+      }
+    }
+  };
+  /* Rat::send's lookup when the window is 0 (rat-templates.cc:13-18): the memory has not changed
+   * since the sender's last lookup, so it returns the same leaf and the same window/intersend;
+   * only the use count moves (and the trace gets a record). */
+  auto zero_window_lookups = [&](uint32_t acked) {
+    if (COUNT) {
+      uint32_t zm = zero_mask & on_mask;
+      while (zm) { const uint32_t s = __ffs(zm) - 1; zm &= zm - 1; cnt[cold[s].leaf]++; }
+    }
+    if (TRACE) track_senders(acked, zero_mask & on_mask);
+  };
+
+  /* The loop is left at ONE place, its top, and nowhere inside a conditional block (an error only
+   * sets `err` and lets the pass run out): early exits from inside divergent regions keep the
+   * compiler from re-converging the warp behind them, and every phase below then runs once per
+   * group of lanes instead of once per pass. */
+  for (;;) {
+    bool run_link = true;
+    /* ---- next event (network.cc:75-78); the Receiver never holds mail here (it is read in the
+     * pass that delivers it), except when the run ends on a delivery ---- */
     double tn = fmax(t, fmin(min_switch, next_send)); /* SenderGang::next_event_time */
     if (pending) tn = fmin(tn, pend_release);           /* Link::next_event_time */
     if (ddeliv != dtail) tn = fmin(tn, dhead_release);  /* Delay::next_event_time */
-    if (dcons != ddeliv) tn = fmin(tn, t);              /* Receiver::next_event_time */
-    t = tn;
-    if (t > duration) break;
-    iters++;
-    const bool advanced = t > t_prev;
+    {
+      const bool ended = !half && !(t < duration);
+      const bool overshoot = !half && !ended && tn > duration; /* Network::_tickno keeps the overshooting time */
+      if (overshoot) t = tn;
+      if (err || ended || overshoot) break;
+    }
+    if (!half) {
+      t = tn;
+      iters++;
+      const bool advanced = t > t_prev;
+      uint32_t newly_on = 0;
+      bool sends_dirty = false; /* a window or pacing deadline changed in this tick */
 
-    /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
-    uint32_t newly_on = 0;
-    bool sends_dirty = false; /* a window or pacing deadline changed in this tick */
-    if (min_switch <= t) {
-      sends_dirty = true;
-      flush_share();
-      const uint32_t k0 = __popc(on_mask);
-      double ms = DBL_MAX;
-      for (uint32_t s = 0; s < n && !err; s++) {
-        double nx = nsw[s];
-        if (nx <= t) {
-          if (nx != t) err |= REMY_ERR_ASSERT;
-          SenderCold c = cold[s];
-          bool sending = (on_mask >> s) & 1u;
-          double itick = t_prev;       /* SwitchedSender::internal_tick of a sender that was on */
-          double shr = share[s];
-          do {
-            if (sending) {             /* switch_off (sendergang.cc:151-161) */
-              if (t > itick) { shr = __dadd_rn(shr, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
-              sending = false;
-            } else {                   /* switch_on -> Rat::reset (rat.cc:34-48) */
-              sending = true;
-#pragma unroll
-              for (int a = 0; a < NAX; a++) c.mem[a] = 0;
-              c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0;
-              c.last_send_time = 0;
-              c.largest_ack = (int32_t)(c.packets_sent - 1u);
-              const uint32_t leaf = find_leaf(T, c.mem, err);
-              if (err) break;
-              if (COUNT) cnt[leaf]++;
-              track(leaf, c.mem);
-              DevLeaf w = T.leaves[leaf];
-              if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
-              c.window = whisker_window(0, w.window_multiple, w.window_increment);
-              c.intersend = w.intersend;
-              c.leaf = leaf;
-              itick = t;
+      /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
+      if (min_switch <= t) {
+        sends_dirty = true;
+        flush_share();
+        const uint32_t k0 = __popc(on_mask);
+        double ms = DBL_MAX;
+        for (uint32_t s = 0; s < n && !err; s++) {
+          double nx = nsw[s];
+          if (nx <= t) {
+            if (nx != t) err |= REMY_ERR_ASSERT;
+            SenderCold c = cold[s];
+            bool sending = (on_mask >> s) & 1u;
+            double itick = t_prev;       /* SwitchedSender::internal_tick of a sender that was on */
+            double shr = share[s];
+            do {
+              if (sending) {             /* switch_off (sendergang.cc:151-161) */
+                if (t > itick) { shr = __dadd_rn(shr, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
+                sending = false;
+              } else {                   /* switch_on -> Rat::reset (rat.cc:34-48) */
+                sending = true;
+  #pragma unroll
+                for (int a = 0; a < NAX; a++) c.mem[a] = 0;
+                c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0;
+                c.last_send_time = 0;
+                c.largest_ack = (int32_t)(c.packets_sent - 1u);
+                const uint32_t leaf = find_leaf(T, c.mem, err);
+                if (err) break;
+                if (COUNT) cnt[leaf]++;
+                track(leaf, c.mem);
+                DevLeaf w = T.leaves[leaf];
+                if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
+                c.window = whisker_window(0, w.window_multiple, w.window_increment);
+                c.intersend = w.intersend;
+                c.leaf = leaf;
+                itick = t;
+              }
+              nx = __dadd_rn(nx, exp_sample(prng, __ddiv_rn(1.0, sending ? cfgp->mean_on_duration : cfgp->mean_off_duration)));
+            } while (nx <= t);
+            nsw[s] = nx;
+            cold[s] = c;
+            { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
+            share[s] = shr;
+            const uint32_t bit = 1u << s;
+            if (sending) {
+              on_mask |= bit;
+              if (itick == t) newly_on |= bit;
+              const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
+              hot_send[s * HS] = open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX;
+              open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
+              if (COUNT) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+            } else {
+              on_mask &= ~bit; open_mask &= ~bit;
+              hot_send[s * HS] = DBL_MAX;
+              if (COUNT) zero_mask &= ~bit;
             }
-            nx = __dadd_rn(nx, exp_sample(prng, sending ? stop_rate : start_rate));
-          } while (nx <= t);
-          nsw[s] = nx;
-          cold[s] = c;
-          { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
-          share[s] = shr;
-          const uint32_t bit = 1u << s;
-          if (sending) {
-            on_mask |= bit;
-            if (itick == t) newly_on |= bit;
-            const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
-            hot_send[s * HS] = open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX;
-            open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
-            if (COUNT) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
-          } else {
-            on_mask &= ~bit; open_mask &= ~bit;
-            hot_send[s * HS] = DBL_MAX;
-            if (COUNT) zero_mask &= ~bit;
+          }
+          ms = fmin(ms, nx);
+        }
+        min_switch = ms;
+      }
+      const uint32_t k1 = __popc(on_mask);
+
+      /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
+      prng_before_shuffle = prng;
+      prng = shuffle_skip(prng, n);
+      zero_window_lookups(0);
+
+      /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) ---- */
+      if (advanced) {
+        uint32_t am = on_mask & ~newly_on;
+        if (am) {
+          if (ninc && am != acc_mask) flush_share();
+          acc_mask = am;
+          inc_buf[ninc * HS] = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
+          ninc++;
+        }
+      }
+      t_prev = t;
+      /* flush when the buffer of ANY lane that is here is full: every such lane then flushes in
+       * the same pass (at most INC_BUF increments are pending; a lane adds at most one per pass) */
+      {
+        const uint32_t fullest = __reduce_max_sync(__activemask(), ninc);
+        if (fullest >= INC_BUF) { if (ninc) flush_share(); }
+        else if (fullest == INC_BUF - 1 && ninc) { /* next pass flushes: start fetching the sums */
+          for (uint32_t s0 = 0; s0 < n; s0 += 16) prefetch_line(&share[s0]);
+        }
+      }
+
+      maybe_sends = sends_dirty || next_send <= t;
+      if (maybe_sends && ((pending && pend_release <= t) || (ddeliv != dtail && dhead_release <= t))) run_link = false;
+    }
+
+    bool mail = false;
+    double m_sent = 0; uint32_t m_seq = 0, m_src = 0; /* the packet delivered in this pass (mail is read in the pass that delivers it) */
+    if (run_link) {
+      /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
+      if (pending && pend_release <= t) {
+        if (pend_release != t) err |= REMY_ERR_ASSERT;
+        bool lost;
+        const double loss_p = cfgp->stochastic_loss_rate;
+        if (loss_p > 0.0) lost = canonical(prng) < loss_p;      /* bernoulli (bits/random.h:3739-3750) */
+        else { prng = lcg_mul(prng, 282475249u); lost = false; } /* two draws, 16807^2 */
+        if (!lost) {
+          if (dtail - dcons >= A.delay_cap) err |= REMY_ERR_DELAY_OVERFLOW;
+          else {
+          DelayEnt e; e.release = __dadd_rn(t, cfgp->delay); e.tick_sent = pend_sent; e.seq = pend_seq; e.src = pend_src; e.pad[0] = 0; e.pad[1] = 0;
+          dring[dtail & dmask] = e;
+          if (ddeliv == dtail) { /* it is the head of the delay line right away */
+            dhead_release = e.release; dh_sent = e.tick_sent; dh_seq = e.seq; dh_src = e.src;
+          } else if (dtail - ddeliv == 1) { /* ... or the entry right behind the head */
+            dn_release = e.release; dn_sent = e.tick_sent; dn_seq = e.seq; dn_src = e.src;
+          }
+          dtail++;
           }
         }
-        ms = fmin(ms, nx);
+        pending = false;
       }
-      min_switch = ms;
-      if (err) break;
+      if (!pending && lhead != ltail) {
+        const LinkEnt e = lring[lhead & lmask]; lhead++;
+        if ((lhead & 7u) == 0 && (ltail - lhead) > 8) prefetch_line(&lring[(lhead + 8) & lmask]); /* next 128-byte line of the queue */
+        pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
+      }
+      /* ---- 7. Delay::tick (delay.hh:53-63) -> Receiver::accept ---- */
+      while (ddeliv != dtail && dhead_release <= t) {
+        if (dhead_release != t) err |= REMY_ERR_ASSERT;
+        /* Receiver::accept: the delivered packet's fields move to the mail registers */
+        m_sent = dh_sent; m_seq = dh_seq; m_src = dh_src;
+        ddeliv++;
+        if (ddeliv != dtail) {
+          dhead_release = dn_release; dh_sent = dn_sent; dh_seq = dn_seq; dh_src = dn_src;
+          prefetch_l2(&cold[dh_src]); /* the next ack's sender record: a service time from now */
+          if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
+            const DelayEnt h = dring[(ddeliv + 1) & dmask];
+            dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
+            if (((ddeliv + 1) & 3u) == 3u && (dtail - ddeliv) > 6) prefetch_line(&dring[(ddeliv + 5) & dmask]);
+          }
+        }
+      }
+      /* the tick that reads the mail: same t, no switch can be due, no time passes */
+      mail = (dcons != ddeliv) && (t < duration);
+      if (mail) { iters++; prng_before_shuffle = prng; prng = shuffle_skip(prng, n); }
     }
-    const uint32_t k1 = __popc(on_mask);
-
-    /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
-    const uint32_t prng_before_shuffle = prng;
-    prng = shuffle_skip(prng, n);
 
     /* ---- 3. receive_feedback for every mailbox (sendergang.cc:175-188) ---- */
     /* the sender acked in this tick usually transmits in this tick: its send state is handed
      * over in registers instead of being re-read from HBM */
     uint32_t ak_s = 0xFFFFFFFFu, ak_seq = 0; int32_t ak_lim = 0; double ak_isend = 0;
     uint32_t acked = 0; /* senders whose mailbox was read in this tick */
-    if (dcons != ddeliv) {
-      sends_dirty = true;
+    if (mail) {
       uint32_t done = 0;
       const bool single = (ddeliv - dcons) == 1; /* the usual case: its fields are in m_* */
       for (uint32_t i = dcons; i != ddeliv && !err; i++) {
@@ -527,44 +673,15 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         }
       }
       dcons = ddeliv;
-      if (err) break;
       acked = done;
     }
 
-    /* Rat::send's lookup when the window is 0 (rat-templates.cc:13-18): the
-     * memory has not changed since the sender's last lookup, so it returns the
-     * same leaf and the same window/intersend; only the use count moves. */
-    if (COUNT) {
-      uint32_t zm = zero_mask & on_mask;
-      while (zm) { const uint32_t s = __ffs(zm) - 1; zm &= zm - 1; cnt[cold[s].leaf]++; }
-    }
-    /* trace: the lookups of run_senders happen sender by sender in the shuffled order
-     * (sendergang.cc:83-86 -> TimeSwitchedSender::tick, :190-205): the ack's lookup, then
-     * Rat::send's window-0 lookup, both on the Memory the ack left behind.  The order is
-     * observable (the running medians are order dependent), so the permutation is built
-     * whenever two senders looked something up in this tick. */
-    if (TRACE) {
-      const uint32_t zm = zero_mask & on_mask;
-      uint32_t lk = acked | zm;
-      if (lk) {
-        uint8_t perm[REMY_MAX_SENDERS];
-        const bool ordered = (lk & (lk - 1)) != 0;
-        if (ordered) shuffle_materialise(prng_before_shuffle, n, perm);
-        for (uint32_t i = 0; lk; i++) {
-          uint32_t s;
-          if (ordered) { s = perm[i]; if (!((lk >> s) & 1u)) continue; }
-          else s = __ffs(lk) - 1;
-          lk &= ~(1u << s);
-          const SenderCold c = cold[s];
-          if ((acked >> s) & 1u) track(c.leaf, c.mem);
-          if ((zm >> s) & 1u) track(c.leaf, c.mem);
-        }
-      }
-    }
+    if (mail) zero_window_lookups(acked);
 
-    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34) ----
-     * (the scan is skipped when no deadline is due and nothing changed: next_send stays valid) */
-    if (sends_dirty || next_send <= t) {
+    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34): the sender phase
+     * of the fused tick if mail was read, else of the tick this pass began with (the scan is skipped when
+     * no deadline is due and nothing changed: next_send stays valid) ---- */
+    if (mail || (!half && maybe_sends)) {
       uint32_t ready = 0, ns_sender = 0xFFFFFFFFu;
       double ns = DBL_MAX;
       uint32_t om = open_mask;
@@ -593,7 +710,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           /* Link::accept (link.hh:26-34) */
           if (!pending) {
             pending = true; pend_release = __dadd_rn(t, service); pend_sent = t; pend_seq = seq; pend_src = s;
-          } else if (limit && (ltail - lhead) < limit) {
+          } else if ((ltail - lhead) < cfgp->buffer_size) { /* (a limit of 0 accepts nothing) */
             if (ltail - lhead >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
             LinkEnt e; e.tick_sent = t; e.seq = seq; e.src = s;
             lring[ltail & lmask] = e; ltail++;
@@ -604,69 +721,12 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           if (!open) open_mask &= ~(1u << s);
           if (st < ns) { ns = st; ns_sender = s; }
         }
-        if (err) break;
       }
       next_send = ns;
       if (ns_sender != 0xFFFFFFFFu) prefetch_line(&sendst[ns_sender]); /* what its transmission will read */
     }
 
-    /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) ---- */
-    if (advanced) {
-      uint32_t am = on_mask & ~newly_on;
-      if (am) {
-        if (ninc && am != acc_mask) flush_share();
-        acc_mask = am;
-        inc_buf[ninc * HS] = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
-        ninc++;
-      }
-    }
-    t_prev = t;
-    /* flush on a fixed iteration phase rather than when the buffer fills: every lane of a
-     * warp then flushes in the same loop iteration (at most INC_BUF increments are pending) */
-    if ((iters & (INC_BUF - 1)) == 0 && ninc) flush_share();
-    else if ((iters & (INC_BUF - 1)) == INC_BUF - 1 && ninc) { /* next iteration flushes: start fetching the sums */
-      for (uint32_t s0 = 0; s0 < n; s0 += 16) prefetch_line(&share[s0]);
-    }
-
-    /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
-    if (pending && pend_release <= t) {
-      if (pend_release != t) err |= REMY_ERR_ASSERT;
-      bool lost;
-      if (loss_p > 0.0) lost = canonical(prng) < loss_p;      /* bernoulli (bits/random.h:3739-3750) */
-      else { prng = lcg_mul(prng, 282475249u); lost = false; } /* two draws, 16807^2 */
-      if (!lost) {
-        if (dtail - dcons >= A.delay_cap) { err |= REMY_ERR_DELAY_OVERFLOW; break; }
-        DelayEnt e; e.release = __dadd_rn(t, delay); e.tick_sent = pend_sent; e.seq = pend_seq; e.src = pend_src; e.pad[0] = 0; e.pad[1] = 0;
-        dring[dtail & dmask] = e;
-        if (ddeliv == dtail) { /* it is the head of the delay line right away */
-          dhead_release = e.release; dh_sent = e.tick_sent; dh_seq = e.seq; dh_src = e.src;
-        } else if (dtail - ddeliv == 1) { /* ... or the entry right behind the head */
-          dn_release = e.release; dn_sent = e.tick_sent; dn_seq = e.seq; dn_src = e.src;
-        }
-        dtail++;
-      }
-      pending = false;
-    }
-    if (!pending && lhead != ltail) {
-      const LinkEnt e = lring[lhead & lmask]; lhead++;
-      if ((lhead & 7u) == 0 && (ltail - lhead) > 8) prefetch_line(&lring[(lhead + 8) & lmask]); /* next 128-byte line of the queue */
-      pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
-    }
-    /* ---- 7. Delay::tick (delay.hh:53-63) -> Receiver::accept ---- */
-    while (ddeliv != dtail && dhead_release <= t) {
-      if (dhead_release != t) err |= REMY_ERR_ASSERT;
-      /* Receiver::accept: the delivered packet's fields move to the mail registers */
-      m_sent = dh_sent; m_seq = dh_seq; m_src = dh_src;
-      ddeliv++;
-      if (ddeliv != dtail) {
-        dhead_release = dn_release; dh_sent = dn_sent; dh_seq = dn_seq; dh_src = dn_src;
-        if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
-          const DelayEnt h = dring[(ddeliv + 1) & dmask];
-          dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
-          if (((ddeliv + 1) & 3u) == 3u && (dtail - ddeliv) > 6) prefetch_line(&dring[(ddeliv + 5) & dmask]);
-        }
-      }
-    }
+    half = !run_link;
   }
 
   /* ---- results: Utility::utility (utility.hh:46-60), SenderGang::utility (sendergang.cc:280-293) ---- */

@@ -51,6 +51,15 @@ def test_gpu_simultaneous_sends_and_ring_regrowth(device, oracle):
     assert_same_results(got, want, exact_utility=False, what="burst")
 
 
+def test_gpu_coincident_events(device, oracle):
+    """Timer sends, departures and deliveries on the same instants (see tests/test_kernel_emu.py)."""
+    from test_kernel_emu import coincident_event_batch
+    tree, cfgs, seeds, cands = coincident_event_batch()
+    a = device.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    b = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=16)
+    assert_same_results(a, b, exact_utility=False, what="coincident events")
+
+
 def test_gpu_link_ring_overflow_is_rerun(device, oracle):
     """An unpaced, ever-growing window on an infinite buffer queues far more packets than
     the first-try ring holds; the library re-runs such simulations with larger rings."""

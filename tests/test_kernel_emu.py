@@ -121,3 +121,29 @@ def test_emu_irregular_trees(emu, oracle, kind):
         a = emu.score(tree, cfgs, seeds, want_use_counts=True)
         b = oracle.score(tree, cfgs, seeds, want_use_counts=True, threads=4)
         assert_same_results(a, b, what=f"{kind}/{rep}")
+
+
+def coincident_event_batch():
+    """Pacing intervals that are multiples of the link's service time, zero delay, zero pacing: timer
+    sends, departures and deliveries fall on the same instants, which is where the kernel's fused /
+    split passes must still do the reference's ticks one by one."""
+    rows = []
+    for n in (1, 2, 5, 16, 32):
+        for link, delay in ((1.0, 50.0), (2.0, 100.0), (0.5, 0.0), (1.0, 1.0), (4.0, 25.0)):
+            for buf in (0, 1, 3, 10, abi.BUFFER_INFINITE):
+                rows.append(dict(num_senders=n, link_ppt=link, delay=delay, buffer_size=buf, stochastic_loss_rate=0.0,
+                                 mean_on_duration=1000.0, mean_off_duration=200.0, simulation_ticks=1500.0))
+    cfgs = abi.make_configs(rows)
+    seeds = np.arange(1, len(cfgs) + 1, dtype=np.uint32)
+    acts = ((1, 1.0, 1), (1, 0.5, 1), (1, 2.0, 1), (0.9, 1.0, 2), (1, 0.25, 1), (0.5, 0.0, 4), (1, 3.0, 1), (0.8, 1.0, 32), (1, 0.0, 1))
+    cands = np.zeros(len(acts), dtype=abi.leaf_override_dtype)
+    for k, (mult, inter, incr) in enumerate(acts):
+        cands[k] = (mult, inter, incr, 0)
+    return abi.default_tree(), cfgs, seeds, cands
+
+
+def test_emu_coincident_events(emu, oracle):
+    tree, cfgs, seeds, cands = coincident_event_batch()
+    a = emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    b = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=16)
+    assert_same_results(a, b, what="coincident events")
