@@ -183,7 +183,7 @@ inline uint32_t sender_bucket(uint32_t n)
   return 32;
 }
 
-inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t n_cands)
+inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t n_cands, bool single_pass = false)
 {
   BatchPlan p;
   uint64_t lim_max = 0; double bdp_max = 0; bool any_big = false;
@@ -205,7 +205,7 @@ inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t
   std::vector<uint32_t> bucket(n_cfgs);
   for (uint32_t k = 0; k < n_cfgs; k++) {
     cost[k] = cfgs[k].link_ppt * cfgs[k].simulation_ticks;
-    bucket[k] = sender_bucket(cfgs[k].num_senders);
+    bucket[k] = single_pass ? REMY_MAX_SENDERS : sender_bucket(cfgs[k].num_senders);
   }
   /* instances sorted by config: same num_senders together (same loop trip counts in a
    * warp), longest first (the tail of each pass is made of its shortest simulations) */
@@ -220,7 +220,7 @@ inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t
     const uint32_t bk = bucket[p.order[i] % n_cfgs];
     uint32_t j = i;
     while (j < n_sims && bucket[p.order[j] % n_cfgs] == bk) j++;
-    PassPlan pp; pp.n_max = bk; pp.begin = i; pp.end = j;
+    PassPlan pp; pp.n_max = single_pass ? std::max(p.n_max, 4u) : bk; pp.begin = i; pp.end = j;
     p.passes.push_back(pp);
     i = j;
   }

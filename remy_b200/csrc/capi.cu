@@ -302,7 +302,12 @@ static int create_impl(const RemyFlatTree *tree,
   if (!pt.table.empty()) CU(cudaMemcpyAsync(b->table.p, pt.table.data(), pt.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, g_stream));
 
   /* ---- configs: ring sizes, config-sorted order, passes by sender count ---- */
-  const BatchPlan plan = plan_batch(cfgs, n_cfgs, n_cands);
+  /* One launch over one cost-sorted list (largest sender counts first).  Cutting the batch into a
+   * launch per sender-count bucket (REMY_B200_SINGLE_PASS=0) buys nothing - residency is bound by
+   * registers, not by the per-sender shared memory - and costs a drain per launch: a block leaves
+   * only when its slowest simulation has ended, and single simulations run for seconds. */
+  const char *sp = getenv("REMY_B200_SINGLE_PASS");
+  const BatchPlan plan = plan_batch(cfgs, n_cfgs, n_cands, !(sp && atoi(sp) == 0));
   if (b->want_senders && sender_stride < plan.n_max) return fail(REMY_EINVAL, "sender_stride smaller than the largest num_senders");
   b->delay_cap = plan.delay_cap;
   if (plan.passes.size() > MAX_PASSES) return fail(REMY_EINVAL, "internal: too many passes");
