@@ -7,7 +7,7 @@ workload : BASELINE configs[1] — the default Remy ConfigRange Evaluator pass (
            step 0.25 x rtt 100..200 step 25 x nsrc 1..32 = 800 NetConfigs, on = off = 5000 ms,
            infinite buffer, no loss, fixed WhiskerTree), batched over R evaluator seeds per GPU
            so that one step fills the machine.  One step = one scoring pass over that batch.
-value    : device time of the kernel launches (CUDA events on the launching stream, inside
+value    : device time of the kernel launches (one simulation launch + one overflow scan per step) (CUDA events on the launching stream, inside
            the library), inputs already resident in HBM
 e2e      : the same pass through the one-shot C-ABI call with HOST buffers
            (remy_b200_score_batch: H2D copies, scratch allocation, kernels, D2H results)
@@ -316,9 +316,10 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                              "note": "achieved = SURVEY.md 8d algorithmic bytes (a design that keeps per-sender state in HBM: 44n+32n_on B "
                                      "per event tick + 32 B per packet sent + 240 B per ack) / step time. This kernel caches event minima and "
-                                     "masks in registers/shared memory, so its real DRAM traffic (`traffic`, ncu dram bytes of one step's 4 pass "
-                                     "launches, profiles/traffic.json) is ~12x smaller and `frac` can exceed 1; `dram_gbs` is the HBM bandwidth "
-                                     "actually used. The path is latency/issue bound (ncu: 17% issue slots, 14/32 lanes), not HBM bound."},
+                                     "masks in registers/shared memory, so its real DRAM traffic (`traffic`, ncu dram bytes of the step's one "
+                                     "simulation launch, profiles/traffic.json) is ~9x smaller and `frac` can exceed 1; `dram_gbs` is the HBM "
+                                     "bandwidth actually used. The path is latency/issue bound (ncu --set full, profiles/r01_ncu_full_final.txt: "
+                                     "30% issue slots, 14.4/32 lanes, long-scoreboard 6.0 cycles per issued instruction), not HBM bound."},
                 "cpu_baseline": cpu,
                 "event_ticks_per_sec": ticks_all * args.steps / secs, "sims_per_sec": sims_all * args.steps / secs,
                 "evals_per_sec": sims_all / 800.0 * args.steps / secs, "score_sum": score_all}
