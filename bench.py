@@ -160,7 +160,24 @@ def run_cpu(args, tree, cfgs, seeds):
     return ev / dt, kind, threads, dt, ev, int(sims["event_ticks"].sum())
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints
+    (NCCL's version banner, for instance) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -207,7 +224,7 @@ def main():
                 "event_ticks_per_sec": tot_ticks / tot_t,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ GPU arm
@@ -325,7 +342,7 @@ def main():
                 "evals_per_sec": sims_all / 800.0 * args.steps / secs, "score_sum": score_all}
         if cands is not None:
             line["candidates"] = int(len(cands))
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
