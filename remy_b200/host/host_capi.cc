@@ -208,6 +208,12 @@ int remy_host_track(void *h, uint32_t leaf_index, const double *mem, size_t n)
     return 0;)
 }
 
+/* the sink of Evaluator::score(trace = true) on raw device-format records — no GPU needed */
+int remy_host_feed_records(void *h, const uint64_t *records, uint64_t n, uint32_t words)
+{
+  GUARD(return feed_trace_records(*(WhiskerTree *)h, records, n, words);)
+}
+
 /* median(_acc[axis]) of every leaf: out[leaf * 6 + axis] — no GPU needed */
 int remy_host_medians(void *h, double *out, uint32_t n_leaves)
 {

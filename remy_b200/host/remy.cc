@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <ctime>
 #include <stdexcept>
+#include <thread>
 #include <unistd.h>
 
 namespace remy_b200 {
@@ -550,20 +551,54 @@ namespace {
 struct TrackSink {
   std::vector<Whisker *> leaves;
   std::vector<int> axes; /* axis of record word 1, 2, ... */
+  std::vector<uint32_t> leaf_axes; /* active-axis mask of every leaf */
+  /* One estimator per (leaf, axis), each fed in record order: the pairs are independent of each
+   * other, so a chunk is fed by several host threads, each owning a fixed subset of the pairs. */
+  void feed_range(const uint64_t *rec, uint64_t n, uint32_t words, unsigned part, unsigned parts) const
+  {
+    const size_t na = axes.size();
+    for (uint64_t i = 0; i < n; i++, rec += words) {
+      const uint64_t l = rec[0];
+      const uint32_t mask = leaf_axes[l];
+      for (size_t k = 0; k < na; k++) {
+        if (!(mask & (1u << axes[k])) || (l * na + k) % parts != part) continue;
+        double v; memcpy(&v, &rec[1 + k], sizeof v);
+        leaves[l]->domain()._acc[axes[k]](v);
+      }
+    }
+  }
   static int feed(void *user, uint32_t, const uint64_t *rec, uint64_t n, uint32_t words)
   {
     TrackSink *t = static_cast<TrackSink *>(user);
     if (words != t->axes.size() + 1) return 1;
-    Memory m;
-    for (uint64_t i = 0; i < n; i++, rec += words) {
-      if (rec[0] >= t->leaves.size()) return 1;
-      for (size_t k = 0; k < t->axes.size(); k++) memcpy(&m.mutable_field(t->axes[k]), &rec[1 + k], sizeof(double));
-      t->leaves[rec[0]]->domain().track(m);
-    }
+    for (uint64_t i = 0; i < n; i++) if (rec[i * words] >= t->leaves.size()) return 1;
+    unsigned parts = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (n < 65536) parts = 1;
+    if (parts == 1) { t->feed_range(rec, n, words, 0, 1); return 0; }
+    std::vector<std::thread> th;
+    for (unsigned p = 0; p < parts; p++) th.emplace_back([=]() { t->feed_range(rec, n, words, p, parts); });
+    for (auto &x : th) x.join();
     return 0;
   }
 };
+TrackSink make_sink(WhiskerTree &tree)
+{
+  TrackSink sink;
+  tree.leaves(sink.leaves);
+  uint32_t mask = 0;
+  for (const Whisker *w : sink.leaves) { sink.leaf_axes.push_back(w->domain().axis_mask()); mask |= w->domain().axis_mask(); }
+  std::vector<const WhiskerTree *> stack { &tree }; /* interior nodes count too: the union over ALL nodes, as in the device layout */
+  while (!stack.empty()) { const WhiskerTree *t = stack.back(); stack.pop_back(); mask |= t->_domain.axis_mask(); for (const auto &c : t->_children) stack.push_back(&c); }
+  for (int a = 0; a < REMY_NUM_AXES; a++) if (mask & (1u << a)) sink.axes.push_back(a);
+  return sink;
+}
 } // namespace
+
+int feed_trace_records(WhiskerTree &tree, const uint64_t *records, uint64_t n_records, uint32_t words_per_record)
+{
+  TrackSink sink = make_sink(tree);
+  return TrackSink::feed(&sink, 0, records, n_records, words_per_record);
+}
 
 Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_whiskers, unsigned int prng_seed,
     const std::vector<NetConfig> &configs, bool trace, unsigned int ticks_to_run)
@@ -578,11 +613,7 @@ Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_w
   std::vector<RemySenderResult> snd(cfgs.size() * (size_t)stride);
   std::vector<uint32_t> counts(ft.leaves.size());
   if (trace) { /* Rat(run_whiskers, trace) (src/evaluator.cc:93): every lookup also feeds the leaf's running medians */
-    TrackSink sink;
-    run_whiskers.leaves(sink.leaves);
-    uint32_t mask = 0;
-    for (const auto &nd : ft.nodes) mask |= nd.axis_mask;
-    for (int a = 0; a < REMY_NUM_AXES; a++) if (mask & (1u << a)) sink.axes.push_back(a);
+    TrackSink sink = make_sink(run_whiskers);
     if (remy_b200_score_trace(&tree, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
                               sims.data(), snd.data(), counts.data(), TrackSink::feed, &sink))
       throw std::runtime_error(std::string("remy_b200_score_trace: ") + remy_b200_last_error());

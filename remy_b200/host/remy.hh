@@ -190,6 +190,11 @@ private:
   const Whisker *whisker(const Memory &m) const;
 };
 
+/* Feeds records of remy_b200_score_trace (include/remy_b200.h) to the running medians of the leaves they
+ * name: MemoryRange::track for every record, in order (several host threads, one per subset of the
+ * independent (leaf, axis) estimators).  Returns non-zero on a malformed record. */
+int feed_trace_records(WhiskerTree &tree, const uint64_t *records, uint64_t n_records, uint32_t words_per_record);
+
 /* POD view of a WhiskerTree for the C ABI. */
 struct FlatTree {
   std::vector<RemyTreeNode> nodes; std::vector<RemyLeafAction> leaves;

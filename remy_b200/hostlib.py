@@ -43,6 +43,7 @@ class HostLib:
         L.remy_host_p2_median.argtypes = [_V, C.c_size_t]
         L.remy_host_track.argtypes = [_V, C.c_uint32, _V, C.c_size_t]
         L.remy_host_medians.argtypes = [_V, _V, C.c_uint32]
+        L.remy_host_feed_records.argtypes = [_V, _V, C.c_uint64, C.c_uint32]
         L.remy_host_set_counts.argtypes = [_V, _V, C.c_uint32]
         L.remy_host_split_most_used.argtypes = [_V, C.c_uint]
         L.remy_host_score_trace.argtypes = [_V, _V, C.c_uint32, C.c_uint, C.POINTER(C.c_double)]
@@ -160,6 +161,11 @@ class HostTree:
         """MemoryRange::track of leaf `leaf` with mem[n, 6]."""
         a = np.ascontiguousarray(mem, dtype=np.float64)
         self.host._check(self.host.lib.remy_host_track(self.h, leaf, a.ctypes.data, len(a)) == 0)
+
+    def feed_records(self, records):
+        """records[n, words] uint64 in the layout of remy_b200_score_trace."""
+        a = np.ascontiguousarray(records, dtype=np.uint64)
+        self.host._check(self.host.lib.remy_host_feed_records(self.h, a.ctypes.data, a.shape[0], a.shape[1]) == 0)
 
     def medians(self, n_leaves):
         out = np.zeros((n_leaves, abi.NUM_AXES))

@@ -159,3 +159,26 @@ def test_host_split_equals_reference(host, oracle, reference, name, tree):
     got = ht.flatten()
     assert got.n_leaves == rtree.n_leaves > tree.n_leaves
     assert canon(got) == canon(rtree)
+
+
+def test_host_sink_feeds_in_parallel_like_serial(host, oracle):
+    """The host sink of trace scoring splits the (leaf, axis) estimators over several threads for big
+    chunks; the medians must equal the oracle's strictly serial feed bit for bit."""
+    tree = workloads.load_golden_tree("RemyCC-2014-100x")
+    cfgs, seeds = small_configs(14, 12)
+    cfgs["simulation_ticks"] = 20000
+    _, counts, med = oracle.trace_medians(tree, cfgs, seeds)
+    ht = host.tree_from_flat(tree)
+    recs = []
+    for k in range(len(cfgs)):
+        _, leaf, mem = oracle.trace_sim(tree, cfgs[k], seeds[k])
+        r = np.zeros((len(leaf), 5), dtype=np.uint64)
+        r[:, 0] = leaf
+        r[:, 1:] = np.ascontiguousarray(mem[:, :4]).view(np.uint64)
+        recs.append(r)
+    allrec = np.concatenate(recs)
+    assert len(allrec) > 200000                     # well above the serial threshold
+    half = len(allrec) // 2
+    ht.feed_records(allrec[:half])                  # two chunks, like a log that spans staging buffers
+    ht.feed_records(allrec[half:])
+    assert ht.medians(tree.n_leaves)[:, :4].tobytes() == med[:, :4].tobytes()
