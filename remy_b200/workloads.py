@@ -113,3 +113,18 @@ def random_sweep(n, seed=2026, ticks=1e5):
     out["num_senders"] = nsrc
     out["buffer_size"] = buf.astype(np.uint32)
     return out
+
+
+def config4(ticks_cap=None):
+    """BASELINE configs[3] (SURVEY.md §8d "config 4"): the 105 nsrc = 16 files of the reference's config/
+    directory, decoded by tools/make_config4_fixture.py into tests/golden/config4.json (drop-tail buffers
+    of 10..57 packets and 1e6, stochastic loss 0 / 0.01 / 0.05, on = 5000 ms or 80 ms, off = 500 ms,
+    1e5..3.6e6 ticks).  ticks_cap bounds the run length for CPU checkers."""
+    import json
+    import os
+    rows = json.load(open(os.path.join(abi.REPO_ROOT, "tests", "golden", "config4.json")))
+    for r in rows:
+        r.pop("file")
+        if ticks_cap:
+            r["simulation_ticks"] = min(r["simulation_ticks"], float(ticks_cap))
+    return abi.make_configs(rows)

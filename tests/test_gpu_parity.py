@@ -60,6 +60,24 @@ def test_gpu_coincident_events(device, oracle):
     assert_same_results(a, b, exact_utility=False, what="coincident events")
 
 
+def test_gpu_config4_sweep(device, oracle):
+    """BASELINE configs[3]: the 105 16-sender config files (drop-tail buffers of 10..57 packets and 1e6,
+    loss 0 / 0.01 / 0.05, 80 ms bursts), three candidate actions each, 1e5 ticks (the files' own run
+    lengths go up to 3.6e6 ticks, minutes per simulation for the CPU checker): bit-exact counters, drops
+    included (sent - received - in flight)."""
+    cfgs = workloads.config4(ticks_cap=1e5)
+    seeds = workloads.seeds_for(4, len(cfgs))
+    tree = workloads.load_golden_tree("RemyCC-2014-100x")
+    rng = np.random.default_rng(44)
+    cands = random_candidates(rng, tree, 3)
+    a = device.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    b = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=16)
+    assert (a[0]["error"] == 0).all()
+    dropped = a[0]["packets_sent"] - a[0]["packets_received"] - a[0]["link_queued"] - a[0]["delay_inflight"]
+    assert (dropped >= 0).all() and dropped.sum() > 1e5
+    assert_same_results(a, b, exact_utility=False, what="config4")
+
+
 def test_gpu_link_ring_overflow_is_rerun(device, oracle):
     """An unpaced, ever-growing window on an infinite buffer queues far more packets than
     the first-try ring holds; the library re-runs such simulations with larger rings."""

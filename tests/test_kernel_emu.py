@@ -147,3 +147,16 @@ def test_emu_coincident_events(emu, oracle):
     a = emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
     b = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=16)
     assert_same_results(a, b, what="coincident events")
+
+
+def test_emu_config4_sweep(emu, oracle):
+    """BASELINE configs[3]: all 16-sender config files (finite buffers, stochastic loss, bursty on-times)."""
+    cfgs = workloads.config4(ticks_cap=2500)
+    assert len(cfgs) == 105 and set(cfgs["stochastic_loss_rate"].tolist()) == {0.0, 0.01, 0.05}
+    seeds = workloads.seeds_for(4, len(cfgs))
+    for name in ("default", "RemyCC-2014-100x"):
+        tree = workloads.load_golden_tree(name)
+        a = emu.score(tree, cfgs, seeds, want_use_counts=True)
+        b = oracle.score(tree, cfgs, seeds, want_use_counts=True, threads=16)
+        assert (a[0]["error"] == 0).all() and a[0]["packets_sent"].sum() > a[0]["packets_received"].sum() > 100000
+        assert_same_results(a, b, what="config4 " + name)
