@@ -507,12 +507,17 @@ int remy_b200_score_trace(const RemyFlatTree *tree,
   /* 2. writing runs over consecutive groups of configs whose log fits the budget */
   size_t free_b = 0, total_b = 0;
   { std::lock_guard<std::mutex> lk(g_mu); CU(cudaSetDevice(g_device)); CU(cudaMemGetInfo(&free_b, &total_b)); }
+  if (n_cfgs == 0) return 0;
   uint64_t budget = std::min<uint64_t>(free_b / 3, (uint64_t)32 << 30);
   if (const char *e = getenv("REMY_B200_TRACE_LOG_BYTES")) { const long long v = atoll(e); if (v > 0) budget = (uint64_t)v; }
   const uint64_t rec_bytes = (uint64_t)words * sizeof(uint64_t);
   const size_t stage_bytes = (size_t)64 << 20;
-  uint64_t *stage = nullptr;
-  { std::lock_guard<std::mutex> lk(g_mu); CU(cudaMallocHost(&stage, stage_bytes)); }
+  struct Pinned { /* freed on every way out */
+    uint64_t *p = nullptr;
+    ~Pinned() { if (p) { std::lock_guard<std::mutex> lk(g_mu); cudaFreeHost(p); } }
+  } pinned;
+  { std::lock_guard<std::mutex> lk(g_mu); CU(cudaMallocHost(&pinned.p, stage_bytes)); }
+  uint64_t *const stage = pinned.p;
   const uint64_t stage_recs = stage_bytes / rec_bytes;
   uint32_t g0 = 0;
   while (g0 < n_cfgs && !rc) {
@@ -551,7 +556,6 @@ int remy_b200_score_trace(const RemyFlatTree *tree,
     remy_b200_batch_destroy(g);
     g0 = g1;
   }
-  { std::lock_guard<std::mutex> lk(g_mu); cudaFreeHost(stage); }
   return rc;
 }
 
