@@ -63,6 +63,7 @@
 #include "evaluator.hh"
 #include "network.cc"
 #include "rat-templates.cc"
+#include "fish-templates.cc"
 #undef private
 #undef protected
 
@@ -360,6 +361,140 @@ extern "C" int remy_ref_trace_split(const RemyFlatTree *tree, const RemyNetConfi
     if (nodes.size() > node_cap || leaves.size() > leaf_cap) return REMY_EINVAL;
     memcpy(out_nodes, nodes.data(), nodes.size() * sizeof(RemyTreeNode));
     memcpy(out_leaves, leaves.data(), leaves.size() * sizeof(RemyLeafAction));
+  }
+  return 0;
+}
+
+/* ---- second sender family: Evaluator<FinTree> / Fish (src/evaluator.cc:105-132) ------------ *
+ * Same shapes as remy_ref_score_batch; a leaf's lambda travels in RemyLeafAction.intersend
+ * (RemyLeafOverride.intersend for candidates).  mode 0 steps the reference's own
+ * Network<SenderGang<Fish, TimeSwitchedSender<Fish>>, ...> exactly like the public score() does
+ * (Fish seed = first draw of the run PRNG, :113) so that counters and the PRNG end state can be read;
+ * mode 1 calls the public static score(). */
+
+namespace {
+
+typedef SenderGang<Fish, TimeSwitchedSender<Fish>> FishGang;
+typedef Network<FishGang, FishGang> FishNetwork;
+
+void build_fin_dna(const RemyFlatTree *t, uint32_t node, const RemyLeafOverride *ov, RemyBuffers::FinTree *out)
+{
+  const RemyTreeNode &nd = t->nodes[node];
+  out->mutable_domain()->CopyFrom(range_dna(nd));
+  if (nd.child_count == 0) {
+    double lambda = t->leaves[nd.leaf_index].intersend;
+    if (ov && ov->leaf_index == nd.leaf_index) lambda = ov->intersend;
+    RemyBuffers::Fin *f = out->mutable_leaf();
+    f->set_lambda(lambda);
+    f->mutable_domain()->CopyFrom(range_dna(nd));
+  } else {
+    for (uint32_t c = 0; c < nd.child_count; c++) build_fin_dna(t, nd.child_begin + c, ov, out->add_children());
+  }
+}
+
+void collect_fin_counts(const FinTree &t, std::vector<unsigned> &counts)
+{
+  if (t.is_leaf()) { counts.push_back(t._leaf.front().count()); return; }
+  for (const auto &c : t._children) collect_fin_counts(c, counts);
+}
+
+void run_fish_whitebox(FinTree &tree, const RemyNetConfig &c, uint32_t seed, RemySimResult *out, RemySenderResult *snd)
+{
+  PRNG run_prng(seed);
+  unsigned int fish_prng_seed(run_prng());
+  const NetConfig x = to_netconfig(c);
+  FishNetwork net(Fish(tree, fish_prng_seed, false), run_prng, x);
+  const double duration = c.simulation_ticks;
+  uint64_t iters = 0;
+  while (net._tickno < duration) { /* src/network.cc:73-84 */
+    net._tickno = std::min(std::min(net._senders.next_event_time(net._tickno),
+                                    std::min(net._link.next_event_time(net._tickno),
+                                             net._stochastic_loss.next_event_time(net._tickno))),
+                           std::min(net._delay.next_event_time(net._tickno),
+                                    net._rec.next_event_time(net._tickno)));
+    if (net._tickno > duration) break;
+    assert(net._tickno < std::numeric_limits<double>::max());
+    net.tick();
+    iters++;
+  }
+  memset(out, 0, sizeof *out);
+  out->utility = net.senders().utility();
+  out->last_tick = net._tickno;
+  out->event_ticks = iters;
+  const unsigned n = net._senders.gang1_.count_senders();
+  for (unsigned i = 0; i < n; i++) {
+    const auto &s = net._senders.gang1_._gang[i];
+    out->packets_sent += (unsigned)s.sender._packets_sent;
+    out->packets_received += s.utility._packets_received;
+    if (snd) {
+      snd[i].tick_share_sending = s.utility._tick_share_sending;
+      snd[i].total_delay = s.utility._total_delay;
+      snd[i].packets_received = s.utility._packets_received;
+      snd[i].packets_sent = (unsigned)s.sender._packets_sent;
+    }
+  }
+  out->link_queued = (uint32_t)(net._link._buffer.size() + net._link._pending_packet._queue.size());
+  uint32_t infl = (uint32_t)net._delay._queue.size();
+  for (const auto &v : net._rec._collector) infl += (uint32_t)v.size();
+  out->delay_inflight = infl;
+  std::ostringstream os; os << run_prng;
+  out->prng_state = (uint32_t)std::stoul(os.str());
+}
+
+} // namespace
+
+extern "C" int remy_ref_score_batch_fish(const RemyFlatTree *tree,
+                                         const RemyLeafOverride *cands, uint32_t n_cands,
+                                         const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                         uint32_t sender_stride,
+                                         RemySimResult *out_sims, RemySenderResult *out_senders,
+                                         uint32_t *out_use_counts, uint32_t n_threads, int mode)
+{
+  if (!tree || !cfgs || !seeds || !out_sims) return REMY_EINVAL;
+  if (!cands) n_cands = 1;
+  const uint32_t total = n_cands * n_cfgs;
+  if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * (size_t)n_cands * tree->n_leaves);
+  std::atomic<uint32_t> next(0);
+  std::mutex mu;
+  auto worker = [&]() {
+    std::vector<RemySenderResult> tmp(4096);
+    for (;;) {
+      const uint32_t s = next.fetch_add(1);
+      if (s >= total) break;
+      const uint32_t c = s / n_cfgs, k = s % n_cfgs;
+      const RemyLeafOverride *ov = (cands && cands[c].leaf_index != REMY_NO_OVERRIDE) ? &cands[c] : nullptr;
+      RemyBuffers::FinTree dna;
+      build_fin_dna(tree, 0, ov, &dna);
+      FinTree t(dna);
+      t.reset_counts();
+      if (mode == 0) run_fish_whitebox(t, cfgs[k], seeds[k], &out_sims[s], tmp.data());
+      else {
+        std::vector<NetConfig> one { to_netconfig(cfgs[k]) };
+        auto outcome = Evaluator<FinTree>::score(t, seeds[k], one, false, (unsigned int)cfgs[k].simulation_ticks);
+        memset(&out_sims[s], 0, sizeof(RemySimResult));
+        out_sims[s].utility = outcome.score;
+        const auto &td = outcome.throughputs_delays.at(0).second;
+        for (size_t i = 0; i < td.size(); i++) { tmp[i].tick_share_sending = td[i].first; tmp[i].total_delay = td[i].second; tmp[i].packets_received = 0; tmp[i].packets_sent = 0; }
+      }
+      if (out_senders) {
+        RemySenderResult *dst = &out_senders[(size_t)s * sender_stride];
+        memset(dst, 0, sizeof(RemySenderResult) * sender_stride);
+        memcpy(dst, tmp.data(), sizeof(RemySenderResult) * std::min(sender_stride, cfgs[k].num_senders));
+      }
+      if (out_use_counts) {
+        std::vector<unsigned> counts;
+        collect_fin_counts(t, counts);
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t l = 0; l < counts.size() && l < tree->n_leaves; l++)
+          out_use_counts[(size_t)c * tree->n_leaves + l] += counts[l];
+      }
+    }
+  };
+  if (n_threads <= 1) worker();
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t i = 0; i < n_threads; i++) th.emplace_back(worker);
+    for (auto &t : th) t.join();
   }
   return 0;
 }

@@ -247,9 +247,18 @@ typedef struct {
 
 typedef struct { double tick_share_sending; unsigned packets_received; double total_delay; } utility_t;
 
+/* Fish (src/fish.hh:16-36): Poisson-paced sender, the second sender family (Evaluator<FinTree>).
+ * Shares memory / packets_sent / flow_id / largest_ack / last_send_time with rat_t. */
+typedef struct {
+  double next_send_time, lambda, max_intersend;
+  prng_t prng;             /* Fish::_prng: every sender's copy starts from the same seed (sendergang.cc:9-26 copies the exemplar) */
+} fish_t;
+#define FISH_BATCH_SIZE 5u  /* Fish::_batch_size (src/fish.cc:20) */
+
 typedef struct {
   double internal_tick, next_switch_tick;
   rat_t rat;
+  fish_t fish;
   utility_t utility;
   int sending;
   unsigned id;
@@ -273,6 +282,7 @@ typedef struct {
   mailbox_t *collector; uint32_t collector_size;
   double tickno;
   uint32_t err;
+  int kind;                /* 0 = Rat over a WhiskerTree, 1 = Fish over a FinTree (leaf lambda in RemyLeafAction.intersend) */
 } net_t;
 
 /* Rat::reset (src/rat.cc:34-48); Memory::reset (src/memory.hh:93). */
@@ -339,6 +349,63 @@ static void rat_send(net_t *N, rat_t *r, unsigned id, double tickno)
   }
 }
 
+/* ---------------------------------------------------------------- Fish ---- */
+/* Fish::_update_lambda / _update_send_time (src/fish.cc:59-70); Exponential::sample with the
+ * sender's own PRNG (src/exponential.hh:22). */
+static void fish_update_lambda(rat_t *r, fish_t *f, double lambda)
+{
+  (void)r;
+  f->lambda = lambda;
+  f->max_intersend = 2.0 / lambda;
+}
+static void fish_update_send_time(rat_t *r, fish_t *f, double tickno)
+{
+  r->last_send_time = tickno;
+  const double x = exp_sample(&f->prng, f->lambda);
+  f->next_send_time = r->last_send_time + FISH_BATCH_SIZE * (x < f->max_intersend ? x : f->max_intersend); /* std::min(sample, max) */
+}
+/* Fish::reset (src/fish.cc:36-48) */
+static void fish_reset(rat_t *r, fish_t *f)
+{
+  memset(&r->memory, 0, sizeof r->memory);
+  r->last_send_time = 0; f->next_send_time = 0; f->lambda = 0; f->max_intersend = 0;
+  r->flow_id++;
+  r->largest_ack = (int)r->packets_sent - 1;
+}
+/* Fish::packets_received (src/fish.cc:26-34) */
+static void fish_packets_received(net_t *N, rat_t *r, fish_t *f, const pkt_t *pk, size_t n)
+{
+  r->packets_received += (unsigned)n;
+  for (size_t i = 0; i < n; i++) memory_packet_received(&r->memory, &pk[i], r->largest_ack, &N->err);
+  const int last = (int)pk[n - 1].seq_num;
+  r->largest_ack = last > r->largest_ack ? last : r->largest_ack;
+  RemyLeafAction w;
+  if (!use_whisker(&N->pol, &r->memory, &w, &N->err)) return; /* FinTree::use_fin (src/fintree.cc:39-57) */
+  fish_update_lambda(r, f, w.intersend);
+  fish_update_send_time(r, f, r->last_send_time);
+}
+/* Fish::next_event_time (src/fish.cc:50-57) */
+static double fish_next_event_time(const fish_t *f, double tickno)
+{
+  return f->next_send_time == 0 ? tickno : f->next_send_time;
+}
+/* Fish::send (src/fish-templates.cc:8-27) */
+static void fish_send(net_t *N, rat_t *r, fish_t *f, unsigned id, double tickno)
+{
+  if (tickno < f->next_send_time) return;
+  if (f->lambda == 0) {
+    RemyLeafAction w;
+    if (!use_whisker(&N->pol, &r->memory, &w, &N->err)) return;
+    fish_update_lambda(r, f, w.intersend);
+  }
+  for (unsigned i = 0; i < FISH_BATCH_SIZE; i++) {
+    pkt_t p; p.src = id; p.tick_sent = tickno; p.tick_received = -1; p.seq_num = r->packets_sent;
+    r->packets_sent++;
+    link_accept(N, &p, tickno);
+  }
+  fish_update_send_time(r, f, tickno);
+}
+
 /* SwitchedSender::accumulate_sending_time_until (src/sendergang.cc:163-173),
  * Utility::sending_duration (src/utility.hh:19). */
 static void accumulate(sender_t *s, double tickno, unsigned num_sending)
@@ -356,7 +423,7 @@ static void switcher(net_t *N, sender_t *s, double tickno, unsigned num_sending)
   while (s->next_switch_tick <= tickno) {
     if (s->next_switch_tick != tickno) N->err |= REMY_ERR_ASSERT; /* sendergang.cc:98 */
     if (s->sending) { accumulate(s, tickno, num_sending); s->sending = 0; }
-    else { s->sending = 1; rat_reset(N, &s->rat); s->internal_tick = tickno; }
+    else { s->sending = 1; if (N->kind) fish_reset(&s->rat, &s->fish); else rat_reset(N, &s->rat); s->internal_tick = tickno; }
     s->next_switch_tick += exp_sample(&N->prng, s->sending ? N->stop_rate : N->start_rate);
     if (N->err & (REMY_ERR_NO_WHISKER | REMY_ERR_NO_CHILD)) return;
   }
@@ -373,11 +440,13 @@ static void sender_tick(net_t *N, sender_t *s, double tickno, unsigned num_sendi
       if (!(mb->a[i].tick_received >= mb->a[i].tick_sent)) N->err |= REMY_ERR_ASSERT;
       s->utility.total_delay += mb->a[i].tick_received - mb->a[i].tick_sent;
     }
-    rat_packets_received(N, &s->rat, mb->a, mb->len);
+    if (N->kind) fish_packets_received(N, &s->rat, &s->fish, mb->a, mb->len);
+    else rat_packets_received(N, &s->rat, mb->a, mb->len);
     mb->len = 0;
   }
   if (s->sending) {
-    rat_send(N, &s->rat, s->id, tickno);
+    if (N->kind) fish_send(N, &s->rat, &s->fish, s->id, tickno);
+    else rat_send(N, &s->rat, s->id, tickno);
     accumulate(s, tickno, num_sending);
   }
 }
@@ -472,11 +541,28 @@ void remy_oracle_run_sim(const RemyFlatTree *tree, const RemyLeafOverride *ov,
   remy_oracle_run_sim_traced(tree, ov, cfg, seed, out, out_senders, use_counts, NULL, NULL);
 }
 
+void remy_oracle_run_sim_kind(const RemyFlatTree *tree, const RemyLeafOverride *ov,
+                              const RemyNetConfig *cfg, uint32_t seed, int kind,
+                              RemySimResult *out, RemySenderResult *out_senders,
+                              uint32_t *use_counts,
+                              void (*track)(void *, uint32_t, const double *), void *track_user);
+
 void remy_oracle_run_sim_traced(const RemyFlatTree *tree, const RemyLeafOverride *ov,
                                 const RemyNetConfig *cfg, uint32_t seed,
                                 RemySimResult *out, RemySenderResult *out_senders,
                                 uint32_t *use_counts,
                                 void (*track)(void *, uint32_t, const double *), void *track_user)
+{
+  remy_oracle_run_sim_kind(tree, ov, cfg, seed, 0, out, out_senders, use_counts, track, track_user);
+}
+
+/* kind 0: Evaluator<WhiskerTree>::score (src/evaluator.cc:77-103); kind 1: Evaluator<FinTree>::score
+ * (src/evaluator.cc:105-132), where the Fish's own PRNG seed is the first draw of the run's PRNG (:113). */
+void remy_oracle_run_sim_kind(const RemyFlatTree *tree, const RemyLeafOverride *ov,
+                              const RemyNetConfig *cfg, uint32_t seed, int kind,
+                              RemySimResult *out, RemySenderResult *out_senders,
+                              uint32_t *use_counts,
+                              void (*track)(void *, uint32_t, const double *), void *track_user)
 {
   memset(out, 0, sizeof *out);
   if (cfg->num_senders == 0 || cfg->num_senders > 4096 || !(cfg->simulation_ticks > 0)
@@ -486,6 +572,8 @@ void remy_oracle_run_sim_traced(const RemyFlatTree *tree, const RemyLeafOverride
   }
   net_t N; memset(&N, 0, sizeof N);
   prng_seed(&N.prng, seed);
+  N.kind = kind;
+  const uint32_t fish_prng_seed = kind ? prng_next(&N.prng) : 0;
   N.pol.tree = tree;
   N.pol.ov = (ov && ov->leaf_index != REMY_NO_OVERRIDE) ? ov : NULL;
   N.pol.use_counts = use_counts;
@@ -500,6 +588,7 @@ void remy_oracle_run_sim_traced(const RemyFlatTree *tree, const RemyLeafOverride
     s->id = i;
     s->next_switch_tick = exp_sample(&N.prng, N.start_rate);
     s->rat.largest_ack = -1;
+    if (kind) prng_seed(&s->fish.prng, fish_prng_seed);
   }
   N.delay = cfg->delay;
   N.service = 1.0 / cfg->link_ppt;
@@ -513,7 +602,7 @@ void remy_oracle_run_sim_traced(const RemyFlatTree *tree, const RemyLeafOverride
     double s_next = DBL_MAX;
     for (uint32_t i = 0; i < N.n; i++) {
       const sender_t *s = &N.gang[i];
-      const double ev = dmin(s->next_switch_tick, s->sending ? rat_next_event_time(&s->rat, N.tickno) : DBL_MAX);
+      const double ev = dmin(s->next_switch_tick, s->sending ? (kind ? fish_next_event_time(&s->fish, N.tickno) : rat_next_event_time(&s->rat, N.tickno)) : DBL_MAX);
       if (ev < s_next) s_next = ev;
     }
     const double link_next = N.pending.len ? N.pending.a[N.pending.head].release : DBL_MAX;
@@ -563,6 +652,7 @@ typedef struct {
   uint32_t sender_stride;
   RemySimResult *out_sims; RemySenderResult *out_senders; uint32_t *out_use_counts;
   uint32_t next; pthread_mutex_t mu;
+  int kind;
 } batch_t;
 
 static void *batch_worker(void *arg)
@@ -578,8 +668,8 @@ static void *batch_worker(void *arg)
     if (s >= total) break;
     const uint32_t c = s / b->n_cfgs, k = s % b->n_cfgs;
     if (local_counts) memset(local_counts, 0, sizeof(uint32_t) * b->tree->n_leaves);
-    remy_oracle_run_sim(b->tree, b->cands ? &b->cands[c] : NULL, &b->cfgs[k], b->seeds[k],
-                        &b->out_sims[s], tmp, local_counts);
+    remy_oracle_run_sim_kind(b->tree, b->cands ? &b->cands[c] : NULL, &b->cfgs[k], b->seeds[k], b->kind,
+                             &b->out_sims[s], tmp, local_counts, NULL, NULL);
     if (b->out_senders) {
       const uint32_t n = b->cfgs[k].num_senders < b->sender_stride ? b->cfgs[k].num_senders : b->sender_stride;
       RemySenderResult *dst = &b->out_senders[(size_t)s * b->sender_stride];
@@ -599,6 +689,13 @@ static void *batch_worker(void *arg)
 
 /* Same shapes as remy_b200_score_batch (include/remy_b200.h), run on
  * `n_threads` host threads pulling (candidate, config) items. */
+int remy_oracle_score_batch_kind(const RemyFlatTree *tree,
+                                 const RemyLeafOverride *cands, uint32_t n_cands,
+                                 const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                 uint32_t sender_stride,
+                                 RemySimResult *out_sims, RemySenderResult *out_senders,
+                                 uint32_t *out_use_counts, uint32_t n_threads, int kind);
+
 int remy_oracle_score_batch(const RemyFlatTree *tree,
                             const RemyLeafOverride *cands, uint32_t n_cands,
                             const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
@@ -606,11 +703,24 @@ int remy_oracle_score_batch(const RemyFlatTree *tree,
                             RemySimResult *out_sims, RemySenderResult *out_senders,
                             uint32_t *out_use_counts, uint32_t n_threads)
 {
+  return remy_oracle_score_batch_kind(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders,
+                                      out_use_counts, n_threads, 0);
+}
+
+/* kind 1 = Fish / FinTree: leaf lambda in RemyLeafAction.intersend (and in RemyLeafOverride.intersend) */
+int remy_oracle_score_batch_kind(const RemyFlatTree *tree,
+                                 const RemyLeafOverride *cands, uint32_t n_cands,
+                                 const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                 uint32_t sender_stride,
+                                 RemySimResult *out_sims, RemySenderResult *out_senders,
+                                 uint32_t *out_use_counts, uint32_t n_threads, int kind)
+{
   if (!tree || !cfgs || !seeds || !out_sims) return REMY_EINVAL;
   if (!cands) n_cands = 1;
   batch_t b; memset(&b, 0, sizeof b);
   b.tree = tree; b.cands = cands; b.n_cands = n_cands; b.cfgs = cfgs; b.seeds = seeds; b.n_cfgs = n_cfgs;
   b.sender_stride = sender_stride; b.out_sims = out_sims; b.out_senders = out_senders; b.out_use_counts = out_use_counts;
+  b.kind = kind;
   pthread_mutex_init(&b.mu, NULL);
   if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * (size_t)n_cands * tree->n_leaves);
   if (n_threads <= 1) {

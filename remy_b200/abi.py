@@ -108,6 +108,47 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_PTR)
 
 
+def _score_with(fn, path, tree, cfgs, seeds, cands, want_senders, want_use_counts, extra):
+    """Call a function with the shape of remy_b200_score_batch plus `extra` (ctype, value) arguments."""
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(FlatTreeC), _PTR, C.c_uint32, _PTR, _PTR, C.c_uint32, C.c_uint32, _PTR, _PTR, _PTR] + [t for t, _ in extra]
+    cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+    n_cands = 1 if cands is None else len(cands)
+    if cands is not None:
+        cands = np.ascontiguousarray(cands, dtype=leaf_override_dtype)
+    n = n_cands * len(cfgs)
+    stride = max(1, min(int(cfgs["num_senders"].max()) if len(cfgs) else 1, 4096))
+    sims = np.zeros(n, dtype=sim_result_dtype)
+    senders = np.zeros((n, stride), dtype=sender_result_dtype) if want_senders else None
+    counts = np.zeros((n_cands, tree.n_leaves), dtype=np.uint32) if want_use_counts else None
+    rc = fn(tree.byref(), _ptr(cands), n_cands, _ptr(cfgs), _ptr(seeds), len(cfgs), stride, _ptr(sims), _ptr(senders), _ptr(counts),
+            *[v for _, v in extra])
+    if rc != 0:
+        raise RuntimeError(f"{path}: returned {rc}")
+    return sims, senders, counts
+
+
+def fin_tree(lambdas, cuts=()):
+    """A FinTree (src/fintree.cc:7-12) over rtt_diff, the Fish's only signal: one fin per interval of
+    [0, 163840) split at `cuts`; a leaf's lambda travels in the `intersend` field."""
+    n = len(lambdas)
+    assert n == len(cuts) + 1
+    nodes = np.zeros(1 if n == 1 else n + 1, dtype=tree_node_dtype)
+    leaves = np.zeros(n, dtype=leaf_action_dtype)
+    for nd in nodes:
+        nd["upper"][:] = 163840.0
+        nd["axis_mask"] = 1 << 4
+    edges = [0.0] + list(cuts) + [163840.0]
+    for i, lam in enumerate(lambdas):
+        leaves[i] = (0.0, lam, 0, 0)
+        if n > 1:
+            nodes[i + 1]["lower"][4], nodes[i + 1]["upper"][4], nodes[i + 1]["leaf_index"] = edges[i], edges[i + 1], i
+    if n > 1:
+        nodes[0]["child_begin"], nodes[0]["child_count"] = 1, n
+    return FlatTree(nodes, leaves)
+
+
 class _ScoreLib:
     """Shared calling convention of remy_b200_score_batch and the two checkers."""
 
@@ -151,6 +192,11 @@ class Oracle(_ScoreLib):
 
     def score(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1):
         return super().score(tree, cfgs, seeds, cands, want_senders, want_use_counts, extra=(threads,))
+
+    def score_fish(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1):
+        """Evaluator<FinTree>::score restated: Fish senders over a FinTree (leaf lambda in `intersend`)."""
+        return _score_with(self.lib.remy_oracle_score_batch_kind, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
+                           [(C.c_uint32, threads), (C.c_int, 1)])
 
     def trace_sim(self, tree, cfg, seed, cap=1 << 22):
         """Every use_whisker call of one simulation, in call order: (sim result, leaf[n], mem[n, 6])."""
@@ -198,6 +244,11 @@ class Reference(_ScoreLib):
 
     def score(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1, mode=0):
         return super().score(tree, cfgs, seeds, cands, want_senders, want_use_counts, extra=(threads, mode))
+
+    def score_fish(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1, mode=0):
+        """The reference's own Fish / FinTree code (src/evaluator.cc:105-132)."""
+        return _score_with(self.lib.remy_ref_score_batch_fish, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
+                           [(C.c_uint32, threads), (C.c_int, mode)])
 
     def trace_split(self, tree, cfgs, seeds, generation=0, split=True):
         """The reference's own trace == true scoring (per config, on one tree) and, if `split`, the
