@@ -178,6 +178,23 @@ void remy_b200_batch_destroy(RemyBatch *batch);
 /* Number of kernel launches performed by the last remy_b200_batch_run. */
 uint32_t remy_b200_batch_launches(const RemyBatch *batch);
 
+/* ---- second sender family: Fish over a FinTree ----------------------------- *
+ * Replaces: Evaluator<FinTree>::score (src/evaluator.cc:105-132): the same network with Fish
+ * senders (src/fish.cc, src/fish-templates.cc) — Poisson-paced batches of five packets whose rate
+ * lambda is looked up in a FinTree (src/fintree.cc) on the rtt_diff signal — instead of Rats.
+ * Same arguments and outputs as remy_b200_score_batch.  The tree is the flattened FinTree; a
+ * leaf's Fin::_lambda (src/fin.hh:13) travels in RemyLeafAction.intersend and a candidate's in
+ * RemyLeafOverride.intersend (window_multiple / window_increment are ignored).  Each
+ * simulation's Fish PRNG seed is the first draw of its run PRNG, as in evaluator.cc:113.
+ */
+int remy_b200_score_batch_fish(const RemyFlatTree *tree,
+                               const RemyLeafOverride *cands, uint32_t n_cands,
+                               const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                               uint32_t sender_stride,
+                               RemySimResult *out_sims,
+                               RemySenderResult *out_senders,
+                               uint32_t *out_use_counts);
+
 /* ---- trace == true scoring ------------------------------------------------ *
  * Replaces: Evaluator<WhiskerTree>::score(tree, trace = true) (src/evaluator.cc:77-103 with
  * Rat::_track set, src/rat.cc:8-20), the call Breeder::apply_best_split makes

@@ -302,6 +302,13 @@ class Device(_ScoreLib):
     def last_error(self):
         return self.lib.remy_b200_last_error().decode()
 
+    def score_fish(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False):
+        """remy_b200_score_batch_fish: Fish senders over a FinTree on the GPU."""
+        try:
+            return _score_with(self.lib.remy_b200_score_batch_fish, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts, [])
+        except RuntimeError as e:
+            raise RuntimeError(f"{e}: {self.last_error()}")
+
     def score_trace(self, tree, cfgs, seeds):
         """remy_b200_score_trace -> (sims, senders, use counts, [(leaf[n], values[n, words - 1]) per config])."""
         sink_t = C.CFUNCTYPE(C.c_int, _PTR, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32)

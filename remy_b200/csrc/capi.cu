@@ -100,6 +100,7 @@ struct RemyBatch {
   uint32_t launches = 0;
   /* trace == true scoring (remy_b200_score_trace): 0 = off, 1 = counting run, 2 = writing run */
   int trace = 0; uint32_t trace_words = 0;
+  bool fish = false; /* Fish senders over a FinTree (remy_b200_score_batch_fish) */
   DevBuf<uint64_t> trace_log, trace_off, out_lookups;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ran = false;
@@ -121,6 +122,7 @@ size_t smem_bytes(const RemyBatch *b, uint32_t n_max, bool with_tree)
 const void *kernel_fn(const RemyBatch *b)
 {
   if (b->trace) return (const void *)remy_sim_kernel<true, true>;
+  if (b->fish) return b->want_counts ? (const void *)remy_sim_kernel<true, false, true> : (const void *)remy_sim_kernel<false, false, true>;
   return b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
 }
 
@@ -204,6 +206,8 @@ int launch(RemyBatch *b, const Scratch &s, size_t smem, bool tree_in_smem, const
   CU(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
   const KernelArgs a = make_args(b, s, tree_in_smem, order, n_work, counter);
   if (b->trace) remy_sim_kernel<true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else if (b->fish && b->want_counts) remy_sim_kernel<true, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else if (b->fish) remy_sim_kernel<false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else remy_sim_kernel<false><<<grid, SIM_BLOCK, smem, stream>>>(a);
   CU(cudaGetLastError());
@@ -242,6 +246,8 @@ int remy_b200_init(int device)
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_device = device; g_sms = prop.multiProcessorCount;
   g_err.clear();
   return 0;
@@ -261,7 +267,7 @@ static int create_impl(const RemyFlatTree *tree,
                        const RemyLeafOverride *cands, uint32_t n_cands,
                        const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
                        uint32_t sender_stride, int want_senders, int want_use_counts, int trace,
-                       RemyBatch **out_batch)
+                       RemyBatch **out_batch, bool fish = false)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!out_batch) return fail(REMY_EINVAL, "out_batch is NULL");
@@ -281,6 +287,7 @@ static int create_impl(const RemyFlatTree *tree,
   b->want_senders = want_senders != 0; b->want_counts = want_use_counts != 0 || trace != 0;
   b->sender_stride = sender_stride;
   b->trace = trace;
+  b->fish = fish;
 
   /* ---- tree -> device layout (validated so the kernel cannot walk off the arrays) ---- */
   PreparedTree pt;
@@ -470,6 +477,23 @@ int remy_b200_score_batch(const RemyFlatTree *tree,
   RemyBatch *b = nullptr;
   int rc = remy_b200_batch_create(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride,
                                   out_senders != nullptr, out_use_counts != nullptr, &b);
+  if (rc) return rc;
+  rc = remy_b200_batch_run(b, nullptr);
+  if (!rc) rc = remy_b200_batch_fetch(b, out_sims, out_senders, out_use_counts);
+  remy_b200_batch_destroy(b);
+  return rc;
+}
+
+/* ---- Fish senders over a FinTree --------------------------------------------------------- */
+int remy_b200_score_batch_fish(const RemyFlatTree *tree,
+                               const RemyLeafOverride *cands, uint32_t n_cands,
+                               const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                               uint32_t sender_stride,
+                               RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts)
+{
+  if (!out_sims && n_cfgs) return fail(REMY_EINVAL, "out_sims is NULL");
+  RemyBatch *b = nullptr;
+  int rc = create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, out_use_counts != nullptr, 0, &b, true);
   if (rc) return rc;
   rc = remy_b200_batch_run(b, nullptr);
   if (!rc) rc = remy_b200_batch_fetch(b, out_sims, out_senders, out_use_counts);

@@ -281,7 +281,16 @@ __device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int
 }
 
 /* ------------------------------------------------------------- the sim ---- */
-template <bool COUNT, bool TRACE = false>
+/* FISH selects the second sender family: Evaluator<FinTree>::score (src/evaluator.cc:105-132) with
+ * Fish senders (src/fish.cc, src/fish-templates.cc) instead of Rats.  A Fish has no window: while on
+ * it sends a batch of FISH_BATCH packets whenever its Poisson deadline is due, and every ack batch
+ * re-draws that deadline from the sender's own PRNG.  Its state reuses the Rat's record:
+ * `intersend` holds Fish::_lambda (0 = not looked up since the reset), `window` the state of
+ * Fish::_prng, the pacing deadline (Fish::_next_send_time, 0 = at once) lives in hot_send[];
+ * SendState mirrors {packets_sent, prng, lambda}. */
+constexpr uint32_t FISH_BATCH = 5; /* Fish::_batch_size (src/fish.cc:20) */
+
+template <bool COUNT, bool TRACE = false, bool FISH = false>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         double *inc_buf, double *hot_send, uint32_t HS, /* per-tick arrays, element i at [i * HS] */
                         double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
@@ -328,6 +337,8 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
 
   uint32_t prng = A.seeds[cfg_i] % LCG_M; /* bits/random.tcc:116-126 */
   if (prng == 0) prng = 1;
+  uint32_t fish_seed = 0;
+  if (FISH) { prng = lcg_next(prng); fish_seed = prng; } /* unsigned int fish_prng_seed( run_prng() ), src/evaluator.cc:113 */
   uint32_t err = 0;
 
   const double duration = cfg.simulation_ticks;
@@ -352,7 +363,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     c.reserved = 0;
     const double first_switch = exp_sample(prng, __ddiv_rn(1.0, cfg.mean_off_duration)); /* sendergang.cc:18-19 */
     nsw[s] = first_switch;
-    c.packets_sent = 0; c.largest_ack = -1; c.window = 0; c.u_received = 0; c.leaf = 0; c.pad = 0;
+    c.packets_sent = 0; c.largest_ack = -1; c.window = FISH ? (int32_t)fish_seed : 0; c.u_received = 0; c.leaf = 0; c.pad = 0;
     cold[s] = c;
     min_switch = fmin(min_switch, first_switch);
     share[s] = 0.0;
@@ -435,6 +446,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
    * since the sender's last lookup, so it returns the same leaf and the same window/intersend;
    * only the use count moves (and the trace gets a record). */
   auto zero_window_lookups = [&](uint32_t acked) {
+    if (FISH) return;
     if (COUNT) {
       uint32_t zm = zero_mask & on_mask;
       while (zm) { const uint32_t s = __ffs(zm) - 1; zm &= zm - 1; cnt[cold[s].leaf]++; }
@@ -491,31 +503,36 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                 c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0;
                 c.last_send_time = 0;
                 c.largest_ack = (int32_t)(c.packets_sent - 1u);
-                const uint32_t leaf = find_leaf(T, c.mem, err);
-                if (err) break;
-                if (COUNT) cnt[leaf]++;
-                track(leaf, c.mem);
-                DevLeaf w = T.leaves[leaf];
-                if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
-                c.window = whisker_window(0, w.window_multiple, w.window_increment);
-                c.intersend = w.intersend;
-                c.leaf = leaf;
+                if (FISH) {              /* Fish::reset (fish.cc:36-48): no lookup, lambda = 0 until the first send or ack */
+                  c.intersend = 0;
+                } else {
+                  const uint32_t leaf = find_leaf(T, c.mem, err);
+                  if (err) break;
+                  if (COUNT) cnt[leaf]++;
+                  track(leaf, c.mem);
+                  DevLeaf w = T.leaves[leaf];
+                  if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
+                  c.window = whisker_window(0, w.window_multiple, w.window_increment);
+                  c.intersend = w.intersend;
+                  c.leaf = leaf;
+                }
                 itick = t;
               }
               nx = __dadd_rn(nx, exp_sample(prng, __ddiv_rn(1.0, sending ? cfgp->mean_on_duration : cfgp->mean_off_duration)));
             } while (nx <= t);
             nsw[s] = nx;
             cold[s] = c;
-            { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
+            { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = FISH ? c.window : c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
             share[s] = shr;
             const uint32_t bit = 1u << s;
             if (sending) {
               on_mask |= bit;
               if (itick == t) newly_on |= bit;
-              const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
-              hot_send[s * HS] = open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX;
+              /* (a sender that is on after its switch tick was reset in it: a Fish then sends at once) */
+              const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
+              hot_send[s * HS] = FISH ? 0.0 : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
               open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
-              if (COUNT) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+              if (COUNT && !FISH) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
             } else {
               on_mask &= ~bit; open_mask &= ~bit;
               hot_send[s * HS] = DBL_MAX;
@@ -673,18 +690,27 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         if (COUNT) cnt[leaf]++;
         DevLeaf w = T.leaves[leaf];
         if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
-        c.window = whisker_window(c.window, w.window_multiple, w.window_increment);
-        c.intersend = w.intersend;
+        double fish_due = 0;
+        if (FISH) { /* Fish::packets_received (fish.cc:26-34): _update_lambda, then _update_send_time(_last_send_time) */
+          c.intersend = w.intersend;
+          uint32_t fp = (uint32_t)c.window;
+          const double x = exp_sample(fp, c.intersend), mx = __ddiv_rn(2.0, c.intersend);
+          c.window = (int32_t)fp;
+          fish_due = __dadd_rn(c.last_send_time, __dmul_rn((double)FISH_BATCH, (mx < x) ? mx : x));
+        } else {
+          c.window = whisker_window(c.window, w.window_multiple, w.window_increment);
+          c.intersend = w.intersend;
+        }
         c.leaf = leaf;
         cold[s] = c;
-        ak_s = s; ak_seq = c.packets_sent; ak_lim = c.largest_ack + 1 + c.window; ak_isend = c.intersend;
+        ak_s = s; ak_seq = c.packets_sent; ak_lim = FISH ? c.window : c.largest_ack + 1 + c.window; ak_isend = c.intersend;
         { SendState ss; ss.packets_sent = ak_seq; ss.lim = ak_lim; ss.intersend = ak_isend; sendst[s] = ss; }
         const uint32_t bit = 1u << s;
         if (on_mask & bit) {
-          const bool open = (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
-          hot_send[s * HS] = open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX;
+          const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
+          hot_send[s * HS] = FISH ? fish_due : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
           open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
-          if (COUNT) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+          if (COUNT && !FISH) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
         }
       }
       dcons = ddeliv;
@@ -719,6 +745,35 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           uint32_t seq; int32_t lim; double isend;
           if (s == ak_s) { seq = ak_seq; lim = ak_lim; isend = ak_isend; ak_seq = seq + 1; }
           else { const SendState ss = sendst[s]; seq = ss.packets_sent; lim = ss.lim; isend = ss.intersend; }
+          if (FISH) { /* Fish::send (fish-templates.cc:8-27) */
+            if (isend == 0) { /* no ack since the reset, so the Memory is still all zero: initial lambda */
+              double zero[NAX];
+#pragma unroll
+              for (int a = 0; a < NAX; a++) zero[a] = 0;
+              const uint32_t leaf = find_leaf(T, zero, err);
+              if (err) break;
+              if (COUNT) cnt[leaf]++;
+              isend = (leaf == ov_leaf) ? A.cands[cand].intersend : T.leaves[leaf].intersend;
+            }
+            for (uint32_t b = 0; b < FISH_BATCH; b++, seq++) { /* Link::accept (link.hh:26-34) for each packet of the batch */
+              if (!pending) {
+                pending = true; pend_release = __dadd_rn(t, service); pend_sent = t; pend_seq = seq; pend_src = s;
+              } else if ((ltail - lhead) < limit) {
+                if (ltail - lhead >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
+                LinkEnt e; e.tick_sent = t; e.seq = seq; e.src = s;
+                lring[ltail & lmask] = e; ltail++;
+              }
+            }
+            if (s == ak_s) ak_seq = seq;
+            uint32_t fp = (uint32_t)lim;
+            const double x = exp_sample(fp, isend), mx = __ddiv_rn(2.0, isend);
+            const double st = __dadd_rn(t, __dmul_rn((double)FISH_BATCH, (mx < x) ? mx : x)); /* _update_send_time(tickno) */
+            c->packets_sent = seq; c->last_send_time = t; c->intersend = isend; c->window = (int32_t)fp;
+            { SendState ss; ss.packets_sent = seq; ss.lim = (int32_t)fp; ss.intersend = isend; sendst[s] = ss; }
+            hot_send[s * HS] = st;
+            if (st < ns) { ns = st; ns_sender = s; }
+            continue;
+          }
           c->packets_sent = seq + 1;
           sendst[s].packets_sent = seq + 1;
           c->last_send_time = t;
@@ -794,7 +849,7 @@ constexpr int SIM_BLOCK = 128;
 
 #ifndef REMY_HOST_EMU
 
-template <bool COUNT, bool TRACE = false>
+template <bool COUNT, bool TRACE = false, bool FISH = false>
 __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -832,7 +887,7 @@ __global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT, TRACE>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
+    run_sim<COUNT, TRACE, FISH>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
   }
 }
 

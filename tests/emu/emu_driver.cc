@@ -13,12 +13,40 @@
 
 using namespace remy;
 
+static int score_batch_kind(const RemyFlatTree *tree,
+                            const RemyLeafOverride *cands, uint32_t n_cands,
+                            const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                            uint32_t sender_stride,
+                            RemySimResult *out_sims, RemySenderResult *out_senders,
+                            uint32_t *out_use_counts, uint32_t link_cap_override, int fish);
+
 extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
                                     const RemyLeafOverride *cands, uint32_t n_cands,
                                     const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
                                     uint32_t sender_stride,
                                     RemySimResult *out_sims, RemySenderResult *out_senders,
                                     uint32_t *out_use_counts, uint32_t link_cap_override)
+{
+  return score_batch_kind(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders, out_use_counts, link_cap_override, 0);
+}
+
+/* the Fish / FinTree variant of the kernel (leaf lambda in RemyLeafAction.intersend) */
+extern "C" int remy_emu_score_batch_fish(const RemyFlatTree *tree,
+                                         const RemyLeafOverride *cands, uint32_t n_cands,
+                                         const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                         uint32_t sender_stride,
+                                         RemySimResult *out_sims, RemySenderResult *out_senders,
+                                         uint32_t *out_use_counts, uint32_t link_cap_override)
+{
+  return score_batch_kind(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders, out_use_counts, link_cap_override, 1);
+}
+
+static int score_batch_kind(const RemyFlatTree *tree,
+                            const RemyLeafOverride *cands, uint32_t n_cands,
+                            const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                            uint32_t sender_stride,
+                            RemySimResult *out_sims, RemySenderResult *out_senders,
+                            uint32_t *out_use_counts, uint32_t link_cap_override, int fish)
 {
   PreparedTree pt;
   if (!prepare_tree(tree, pt).empty()) return REMY_EINVAL;
@@ -47,7 +75,11 @@ extern "C" int remy_emu_score_batch(const RemyFlatTree *tree,
     TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
     std::vector<uint32_t> redo;
     for (uint32_t sim : todo) {
-      if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+      if (fish) {
+        if (out_use_counts) run_sim<true, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        else run_sim<false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
+      }
+      else if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
       else run_sim<false>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
       if (out_sims[sim].error & REMY_ERR_LINK_OVERFLOW) redo.push_back(sim);
     }
