@@ -5,6 +5,7 @@
  */
 #include "remy.hh"
 #include "breeder.hh"
+#include "fish.hh"
 
 #include <cstring>
 #include <stdexcept>
@@ -185,6 +186,92 @@ int remy_host_ratbreeder_improve(void *h, const void *range_bytes, size_t range_
     *score = outcome.score;
     if (stats) { stats[0] = (double)b.candidates_scored; stats[1] = (double)b.batches; }
     return 0;)
+}
+
+/* ---- Fish / FinTree (fish.hh) ---- */
+void *remy_host_fintree_default(void) { return new FinTree(); }
+void *remy_host_fintree_parse(const void *data, size_t size)
+{
+  try { return new FinTree(FinTree::parse(data, size)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+void remy_host_fintree_free(void *h) { delete (FinTree *)h; }
+static FinTree fin_from_flat(const RemyTreeNode *nodes, const RemyLeafAction *leaves, uint32_t i)
+{
+  FinTree t; t._leaf.clear();
+  Memory lo, hi;
+  for (unsigned a = 0; a < REMY_NUM_AXES; a++) { lo.f[a] = nodes[i].lower[a]; hi.f[a] = nodes[i].upper[a]; }
+  std::vector<int> axes;
+  for (int a = 0; a < REMY_NUM_AXES; a++) if (nodes[i].axis_mask & (1u << a)) axes.push_back(a);
+  t._domain = MemoryRange(lo, hi, axes);
+  if (nodes[i].child_count == 0) {
+    Fin f(leaves[nodes[i].leaf_index].intersend, t._domain);
+    f._generation = leaves[nodes[i].leaf_index].generation;
+    t._leaf.push_back(f);
+  } else {
+    for (uint32_t c = 0; c < nodes[i].child_count; c++) t._children.push_back(fin_from_flat(nodes, leaves, nodes[i].child_begin + c));
+  }
+  return t;
+}
+void *remy_host_fintree_from_flat(const RemyFlatTree *flat)
+{
+  try { return new FinTree(fin_from_flat(flat->nodes, flat->leaves, 0)); } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+long remy_host_fintree_serialize(void *h, char *buf, size_t cap) { GUARD(return copy_out(((FinTree *)h)->DNA(), buf, cap);) }
+long remy_host_fintree_str(void *h, char *buf, size_t cap) { GUARD(return copy_out(((FinTree *)h)->str(), buf, cap);) }
+int remy_host_fintree_flatten(void *h, RemyTreeNode *nodes, uint32_t cap_nodes, RemyLeafAction *leaves, uint32_t cap_leaves,
+                              uint32_t *n_nodes, uint32_t *n_leaves)
+{
+  GUARD(
+    const FlatTree f = flatten(*(FinTree *)h);
+    *n_nodes = (uint32_t)f.nodes.size(); *n_leaves = (uint32_t)f.leaves.size();
+    if (nodes && f.nodes.size() <= cap_nodes) memcpy(nodes, f.nodes.data(), f.nodes.size() * sizeof(RemyTreeNode));
+    if (leaves && f.leaves.size() <= cap_leaves) memcpy(leaves, f.leaves.data(), f.leaves.size() * sizeof(RemyLeafAction));
+    return 0;)
+}
+/* Fin::next_generation of leaf `leaf_index` -> lambdas; returns the count */
+long remy_host_fin_next_generation(void *h, uint32_t leaf_index, double *out, uint32_t cap)
+{
+  GUARD(
+    std::vector<const Fin *> lv; ((FinTree *)h)->leaves(lv);
+    if (leaf_index >= lv.size()) throw std::runtime_error("leaf index out of range");
+    const std::vector<Fin> gen = lv[leaf_index]->next_generation();
+    for (size_t i = 0; i < gen.size() && i < cap; i++) out[i] = gen[i].lambda();
+    return (long)gen.size();)
+}
+/* Evaluator<FinTree>::score(tree, trace = false, carefulness) — needs a GPU */
+int remy_host_fish_score(void *h, const void *range_bytes, size_t range_size, unsigned int prng_seed, double carefulness,
+                         double *score, uint32_t *use_counts, uint32_t n_counts)
+{
+  GUARD(
+    FinTree &t = *(FinTree *)h;
+    Evaluator<FinTree> e(ConfigRange::parse(range_bytes, range_size), prng_seed);
+    const auto out = e.score(t, false, carefulness);
+    *score = out.score;
+    std::vector<const Fin *> lv; out.used_actions.leaves(lv);
+    for (size_t i = 0; i < lv.size() && i < n_counts; i++) use_counts[i] = lv[i]->count();
+    return 0;)
+}
+/* FinImprover::improve on leaf `leaf_index`, repeated until the score stops rising (src/fishbreeder.cc:39-49) — needs a GPU.
+ * out = {score_to_beat, chosen lambda, candidates scored, batches}; returns the number of improve() calls */
+long remy_host_improve_fin(void *h, const void *range_bytes, size_t range_size, unsigned int prng_seed, uint32_t leaf_index, double *out)
+{
+  GUARD(
+    FinTree &t = *(FinTree *)h;
+    std::vector<const Fin *> lv; t.leaves(lv);
+    if (leaf_index >= lv.size()) throw std::runtime_error("leaf index out of range");
+    Evaluator<FinTree> e(ConfigRange::parse(range_bytes, range_size), prng_seed);
+    auto outcome = e.score(t);
+    FinImprover improver(e, t, outcome.score);
+    Fin f = *lv[leaf_index];
+    double score_to_beat = outcome.score;
+    long calls = 0;
+    for (;;) {
+      const double ns = improver.improve(f); calls++;
+      if (ns == score_to_beat) break;
+      score_to_beat = ns;
+    }
+    out[0] = score_to_beat; out[1] = f.lambda(); out[2] = (double)improver.candidates_scored; out[3] = (double)improver.batches;
+    return calls;)
 }
 
 /* ---- trace == true ---- */

@@ -39,6 +39,20 @@ class HostLib:
         L.remy_host_improve_whisker.restype = C.c_long
         L.remy_host_improve_whisker.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint32, _V]
         L.remy_host_ratbreeder_improve.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_double), _V]
+        for name in ("remy_host_fintree_default", "remy_host_fintree_parse", "remy_host_fintree_from_flat"):
+            getattr(L, name).restype = _V
+        L.remy_host_fintree_parse.argtypes = [C.c_char_p, C.c_size_t]
+        L.remy_host_fintree_from_flat.argtypes = [C.POINTER(abi.FlatTreeC)]
+        L.remy_host_fintree_free.argtypes = [_V]
+        for name in ("remy_host_fintree_serialize", "remy_host_fintree_str"):
+            getattr(L, name).restype = C.c_long
+            getattr(L, name).argtypes = [_V, C.c_char_p, C.c_size_t]
+        L.remy_host_fintree_flatten.argtypes = [_V, _V, C.c_uint32, _V, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.remy_host_fin_next_generation.restype = C.c_long
+        L.remy_host_fin_next_generation.argtypes = [_V, C.c_uint32, _V, C.c_uint32]
+        L.remy_host_fish_score.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.POINTER(C.c_double), _V, C.c_uint32]
+        L.remy_host_improve_fin.restype = C.c_long
+        L.remy_host_improve_fin.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint32, _V]
         L.remy_host_p2_median.restype = C.c_double
         L.remy_host_p2_median.argtypes = [_V, C.c_size_t]
         L.remy_host_track.argtypes = [_V, C.c_uint32, _V, C.c_size_t]
@@ -82,6 +96,19 @@ class HostLib:
         self._check(fn(*args, buf, n) == n)
         return buf.raw[:n]
 
+    def fintree_default(self):
+        return HostFinTree(self, self.lib.remy_host_fintree_default())
+
+    def fintree_parse(self, data):
+        h = self.lib.remy_host_fintree_parse(data, len(data))
+        self._check(h)
+        return HostFinTree(self, h)
+
+    def fintree_from_flat(self, flat):
+        h = self.lib.remy_host_fintree_from_flat(flat.byref())
+        self._check(h)
+        return HostFinTree(self, h)
+
     def solve_problem(self, problem):
         """Evaluator::parse_problem_and_evaluate -> AnswerBuffers.Outcome bytes (needs a GPU)."""
         return self._bytes_call(self.lib.remy_host_solve_problem, problem, len(problem))
@@ -96,6 +123,63 @@ class HostLib:
         n = self.lib.remy_host_config_range_expand(range_bytes, len(range_bytes), carefulness, out.ctypes.data, len(out), dna, 4096, C.byref(n_dna))
         self._check(n >= 0)
         return out[:n].copy(), dna.raw[:n_dna.value]
+
+
+class HostFinTree:
+    """FinTree (remy_b200/host/fish.hh) behind the C wrappers."""
+
+    def __init__(self, host, handle):
+        self.host, self.h = host, handle
+
+    def __del__(self):
+        if self.h:
+            self.host.lib.remy_host_fintree_free(self.h)
+            self.h = None
+
+    def _string(self, fn):
+        n = fn(self.h, None, 0)
+        self.host._check(n >= 0)
+        buf = C.create_string_buffer(n + 1)
+        fn(self.h, buf, n)
+        return buf.raw[:n]
+
+    def serialize(self):
+        return self._string(self.host.lib.remy_host_fintree_serialize)
+
+    def str(self):
+        return self._string(self.host.lib.remy_host_fintree_str).decode()
+
+    def flatten(self):
+        nn, nl = C.c_uint32(0), C.c_uint32(0)
+        self.host._check(self.host.lib.remy_host_fintree_flatten(self.h, None, 0, None, 0, C.byref(nn), C.byref(nl)) == 0)
+        nodes = np.zeros(nn.value, dtype=abi.tree_node_dtype)
+        leaves = np.zeros(nl.value, dtype=abi.leaf_action_dtype)
+        self.host._check(self.host.lib.remy_host_fintree_flatten(self.h, nodes.ctypes.data, len(nodes), leaves.ctypes.data, len(leaves),
+                                                                 C.byref(nn), C.byref(nl)) == 0)
+        return abi.FlatTree(nodes, leaves)
+
+    def next_generation(self, leaf):
+        out = np.zeros(64, dtype=np.float64)
+        n = self.host.lib.remy_host_fin_next_generation(self.h, leaf, out.ctypes.data, len(out))
+        self.host._check(n >= 0)
+        return out[:n].copy()
+
+    def score(self, range_bytes, prng_seed, carefulness=1.0):
+        """Evaluator<FinTree>::score (needs a GPU) -> (score, use counts)."""
+        flat = self.flatten()
+        score = C.c_double(0)
+        counts = np.zeros(flat.n_leaves, dtype=np.uint32)
+        rc = self.host.lib.remy_host_fish_score(self.h, range_bytes, len(range_bytes), prng_seed, carefulness, C.byref(score),
+                                                counts.ctypes.data, len(counts))
+        self.host._check(rc == 0)
+        return score.value, counts
+
+    def improve_fin(self, range_bytes, prng_seed, leaf):
+        """FinImprover::improve until the score stops rising -> (calls, score, lambda, candidates, batches)."""
+        out = np.zeros(4, dtype=np.float64)
+        n = self.host.lib.remy_host_improve_fin(self.h, range_bytes, len(range_bytes), prng_seed, leaf, out.ctypes.data)
+        self.host._check(n >= 0)
+        return int(n), float(out[0]), float(out[1]), int(out[2]), int(out[3])
 
 
 class HostTree:

@@ -25,6 +25,9 @@ DNA = {
                   (4, "link_ppt", "double", 0), (5, "delay", "double", 0), (6, "buffer_size", "uint32", 0),
                   (7, "stochastic_loss_rate", "double", 0), (8, "simulation_ticks", "uint32", 0)],
     "ConfigVector": [(81, "config", "NetConfig", 1)],
+    "Fin": [(37, "lambda", "double", 0), (38, "domain", "MemoryRange", 0)],
+    "FinTree": [(90, "domain", "MemoryRange", 0), (91, "children", "FinTree", 1), (92, "leaf", "Fin", 0),
+                (93, "config", "ConfigRange", 0), (94, "optimizer", "OptimizationSettings", 0), (95, "configvector", "ConfigVector", 0)],
     "WhiskerTree": [(1, "domain", "MemoryRange", 0), (2, "children", "WhiskerTree", 1), (3, "leaf", "Whisker", 0),
                     (4, "config", "ConfigRange", 0), (5, "optimizer", "OptimizationSettings", 0), (6, "configvector", "ConfigVector", 0)],
 }
@@ -60,5 +63,5 @@ def classes():
     pool.Add(_file("answer.proto", "AnswerBuffers", ANSWER, ["dna.proto"]))
     pool.Add(_file("problem.proto", "ProblemBuffers", PROBLEM, ["dna.proto"]))
     get = lambda full: message_factory.GetMessageClass(pool.FindMessageTypeByName(full))
-    return {"WhiskerTree": get("RemyBuffers.WhiskerTree"), "ConfigRange": get("RemyBuffers.ConfigRange"),
+    return {"FinTree": get("RemyBuffers.FinTree"), "WhiskerTree": get("RemyBuffers.WhiskerTree"), "ConfigRange": get("RemyBuffers.ConfigRange"),
             "NetConfig": get("RemyBuffers.NetConfig"), "Problem": get("ProblemBuffers.Problem"), "Outcome": get("AnswerBuffers.Outcome")}

@@ -72,3 +72,121 @@ def test_gpu_fish_equals_oracle(device, oracle):
         b = oracle.score_fish(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=16)
         assert (a[0]["error"] == 0).all()
         assert_same_results(a, b, exact_utility=False, what="fish (GPU)")
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    from helpers import ROOT
+    from remy_b200 import hostlib
+    if not os.path.exists(os.path.join(ROOT, "remy_b200", "csrc", "libremy_b200.so")):
+        built.build_cuda()
+    built.build_host()
+    return hostlib.HostLib()
+
+
+def test_host_fintree_wire_format_and_generation(host):
+    """FinTree / Fin (src/fintree.cc, src/fin.cc) on the host: default tree, RemyBuffers.FinTree bytes
+    (fields 90-92, 37-38) cross-checked against python-protobuf, flatten() for the C ABI, Fin::next_generation."""
+    import pb_schema
+    t = host.fintree_default()
+    raw = t.serialize()
+    FinTreeMsg = pb_schema.classes()["FinTree"]
+    msg = FinTreeMsg()
+    msg.ParseFromString(raw)
+    assert msg.SerializeToString() == raw
+    assert list(msg.domain.active_axis) == [4] and msg.domain.upper.rtt_diff == 163840.0
+    assert getattr(msg.leaf, "lambda") == 5.0
+    flat = t.flatten()
+    want = abi.fin_tree([5.0])
+    assert flat.nodes.tobytes() == want.nodes.tobytes() and flat.leaves["intersend"][0] == 5.0
+    # a three-fin tree built with python-protobuf parses, flattens and re-serialises byte for byte
+    m = FinTreeMsg()
+    m.domain.CopyFrom(msg.domain)
+    for lo, hi, lam in ((0.0, 2.0, 5.0), (2.0, 20.0, 1.0), (20.0, 163840.0, 0.3)):
+        c = m.children.add()
+        c.domain.CopyFrom(msg.domain)
+        c.domain.lower.rtt_diff, c.domain.upper.rtt_diff = lo, hi
+        setattr(c.leaf, "lambda", lam)
+        c.leaf.domain.CopyFrom(c.domain)
+    raw3 = m.SerializeToString()
+    t3 = host.fintree_parse(raw3)
+    assert t3.serialize() == raw3
+    f3 = t3.flatten()
+    w3 = abi.fin_tree([5.0, 1.0, 0.3], [2.0, 20.0])
+    assert f3.nodes.tobytes() == w3.nodes.tobytes() and f3.leaves["intersend"].tolist() == [5.0, 1.0, 0.3]
+    assert "lambda=1.000000" in t3.str()
+    # Fin::next_generation: value, then +-0.01 * 4^k up to 3 inside [0.01, 30], rounded down to 1e-4 (src/fin.cc:33-54,64-67)
+    got = t.next_generation(0).tolist()
+    want = [5.0]
+    c = 0.01
+    while c <= 3:
+        for v in (5.0 + c, 5.0 - c):
+            if 0.01 <= v <= 30:
+                want.append(v)
+        c *= 4
+    assert got == [(1.0 / 10000.0) * int(10000 * v) for v in want] and len(got) == 11
+
+
+@pytest.mark.gpu
+def test_gpu_host_fish_evaluator_and_improver(host, device, oracle):
+    """Evaluator<FinTree>::score and FinImprover::improve on the GPU path against the oracle and an
+    oracle-driven restatement of the improver's control flow (src/breeder.cc:79-150)."""
+    from remy_b200 import hostlib, workloads
+    inf = float(abi.BUFFER_INFINITE)
+    raw = hostlib.encode_config_range(link=(1, 2, 0.5), rtt=(100, 150, 50), nsrc=(1, 9, 4), buf=(50, 50, 0),
+                                      off=(0, 0, 0), on=(1e9, 1e9, 0), ticks=100000)
+    cfgs, _ = host.expand(raw)
+    assert len(cfgs) == 3 * 2 * 3
+    flat = abi.fin_tree([5.0, 1.0, 0.3], [2.0, 20.0])
+    tree = host.fintree_from_flat(flat)
+    seed = 31
+    seeds = workloads.seeds_for(seed, len(cfgs))
+    score, counts = tree.score(raw, seed)
+    sims, _, want_counts = oracle.score_fish(flat, cfgs, seeds, want_use_counts=True, threads=16)
+    want = 0.0
+    for u in sims["utility"]:
+        want += float(u)
+    assert abs(score - want) <= 1e-9 * abs(want) and (counts == want_counts[0]).all()
+
+    def score_many(lams, c):
+        cands = np.zeros(len(lams), dtype=abi.leaf_override_dtype)
+        for i, lam in enumerate(lams):
+            cands[i] = (0, lam, 0, 0)
+        s, _, _ = oracle.score_fish(flat, c, seeds, cands=cands, want_senders=False, threads=16)
+        return [sum(float(u) for u in s["utility"][i * len(c):(i + 1) * len(c)]) for i in range(len(lams))]
+
+    cfgs_fast, _ = host.expand(raw, carefulness=0.1)
+    calls, got_score, got_lambda, n_scored, batches = tree.improve_fin(raw, seed, 0)
+    lam, best, cache, want_calls = 5.0, want, {}, 0
+    while True:
+        want_calls += 1
+        alts = [lam]
+        c = 0.01
+        while c <= 3:
+            for v in (lam + c, lam - c):
+                if 0.01 <= v <= 30:
+                    alts.append(v)
+            c *= 4
+        alts = [(1.0 / 10000.0) * int(10000 * v) for v in alts]
+        fast = [cache[a] if a in cache else None for a in alts]
+        fresh = [a for a, f in zip(alts, fast) if f is None]
+        for a, s in zip(fresh, score_many(fresh, cfgs_fast) if fresh else []):
+            fast[alts.index(a)] = s
+        fast = [f if f is not None else cache[a] for a, f in zip(alts, fast)]
+        lower = min(best * 1.05, best * 0.95)
+        srt = sorted(fast, reverse=True)
+        cutoff = max(lower, srt[int(np.ceil(len(srt) * (1.0 - (1 - 0.5)))) - 1])
+        top = [a for a, f in zip(alts, fast) if f >= cutoff]
+        fresh = [a for a in top if a not in cache]
+        full = dict(zip(fresh, score_many(fresh, cfgs) if fresh else []))
+        before = best
+        for a in top:
+            s = full[a] if a in full else cache[a]
+            if a in full:
+                cache[a] = s
+            if s > best:
+                best, lam = s, a
+        if best == before:
+            break
+    assert calls == want_calls and got_lambda == lam and abs(got_score - best) <= 1e-9 * abs(best)
+    assert batches <= 2 * calls
