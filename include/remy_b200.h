@@ -224,6 +224,15 @@ int remy_b200_score_trace(const RemyFlatTree *tree,
                           RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
                           RemyTraceSink sink, void *user);
 
+/* The same for Fish senders over a FinTree (Evaluator<FinTree>::score(..., trace = true, ...)): a
+ * Fish looks its lambda up on every ack batch and at the first send after a reset
+ * (src/fish.cc:26-34, src/fish-templates.cc:14-18). */
+int remy_b200_score_trace_fish(const RemyFlatTree *tree,
+                               const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                               uint32_t sender_stride,
+                               RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
+                               RemyTraceSink sink, void *user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -811,13 +811,18 @@ static void trace_log_cb(void *user, uint32_t leaf, const double *mem)
   if (t->n < t->cap) { double *r = t->out + 7 * t->n; r[0] = (double)leaf; for (int a = 0; a < REMY_NUM_AXES; a++) r[1 + a] = mem[a]; }
   t->n++;
 }
-uint64_t remy_oracle_trace_sim(const RemyFlatTree *tree, const RemyNetConfig *cfg, uint32_t seed,
-                               RemySimResult *out_sim, double *out, uint64_t cap)
+uint64_t remy_oracle_trace_sim_kind(const RemyFlatTree *tree, const RemyNetConfig *cfg, uint32_t seed, int kind,
+                                    RemySimResult *out_sim, double *out, uint64_t cap)
 {
   trace_log_t t = { out, cap, 0 };
   RemySimResult tmp;
-  remy_oracle_run_sim_traced(tree, NULL, cfg, seed, out_sim ? out_sim : &tmp, NULL, NULL, trace_log_cb, &t);
+  remy_oracle_run_sim_kind(tree, NULL, cfg, seed, kind, out_sim ? out_sim : &tmp, NULL, NULL, trace_log_cb, &t);
   return t.n;
+}
+uint64_t remy_oracle_trace_sim(const RemyFlatTree *tree, const RemyNetConfig *cfg, uint32_t seed,
+                               RemySimResult *out_sim, double *out, uint64_t cap)
+{
+  return remy_oracle_trace_sim_kind(tree, cfg, seed, 0, out_sim, out, cap);
 }
 
 /* Evaluator::score(tree, seed_k, {config_k}, trace = true, ticks) for k = 0..n_cfgs-1 on ONE
@@ -832,8 +837,15 @@ static void trace_acc_cb(void *user, uint32_t leaf, const double *mem)
   for (int a = 0; a < REMY_NUM_AXES; a++)
     if (t->leaf_axes[leaf] & (1u << a)) remy_oracle_p2_add(&t->acc[(size_t)leaf * REMY_NUM_AXES + a], mem[a]);
 }
+int remy_oracle_trace_medians_kind(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs, int kind,
+                                   RemySimResult *out_sims, uint32_t *out_use_counts, p2_t *acc);
 int remy_oracle_trace_medians(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
                               RemySimResult *out_sims, uint32_t *out_use_counts, p2_t *acc)
+{
+  return remy_oracle_trace_medians_kind(tree, cfgs, seeds, n_cfgs, 0, out_sims, out_use_counts, acc);
+}
+int remy_oracle_trace_medians_kind(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs, int kind,
+                                   RemySimResult *out_sims, uint32_t *out_use_counts, p2_t *acc)
 {
   uint32_t *leaf_axes = (uint32_t *)calloc(tree->n_leaves, sizeof(uint32_t));
   for (uint32_t i = 0; i < tree->n_nodes; i++)
@@ -841,7 +853,7 @@ int remy_oracle_trace_medians(const RemyFlatTree *tree, const RemyNetConfig *cfg
   trace_acc_t t = { tree, leaf_axes, acc };
   if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * tree->n_leaves);
   for (uint32_t k = 0; k < n_cfgs; k++)
-    remy_oracle_run_sim_traced(tree, NULL, &cfgs[k], seeds[k], &out_sims[k], NULL, out_use_counts, trace_acc_cb, &t);
+    remy_oracle_run_sim_kind(tree, NULL, &cfgs[k], seeds[k], kind, &out_sims[k], NULL, out_use_counts, trace_acc_cb, &t);
   free(leaf_axes);
   return 0;
 }

@@ -198,21 +198,21 @@ class Oracle(_ScoreLib):
         return _score_with(self.lib.remy_oracle_score_batch_kind, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
                            [(C.c_uint32, threads), (C.c_int, 1)])
 
-    def trace_sim(self, tree, cfg, seed, cap=1 << 22):
-        """Every use_whisker call of one simulation, in call order: (sim result, leaf[n], mem[n, 6])."""
-        f = self.lib.remy_oracle_trace_sim
+    def trace_sim(self, tree, cfg, seed, cap=1 << 22, fish=False):
+        """Every use_whisker / use_fin call of one simulation, in call order: (sim result, leaf[n], mem[n, 6])."""
+        f = self.lib.remy_oracle_trace_sim_kind
         f.restype = C.c_uint64
-        f.argtypes = [C.POINTER(FlatTreeC), _PTR, C.c_uint32, _PTR, _PTR, C.c_uint64]
+        f.argtypes = [C.POINTER(FlatTreeC), _PTR, C.c_uint32, C.c_int, _PTR, _PTR, C.c_uint64]
         cfg = np.ascontiguousarray(cfg, dtype=net_config_dtype).reshape(1)
         sim = np.zeros(1, dtype=sim_result_dtype)
         buf = np.zeros(cap * 7, dtype=np.float64)
-        n = int(f(tree.byref(), _ptr(cfg), int(seed), _ptr(sim), _ptr(buf), cap))
+        n = int(f(tree.byref(), _ptr(cfg), int(seed), int(fish), _ptr(sim), _ptr(buf), cap))
         if n > cap:
-            return self.trace_sim(tree, cfg, seed, cap=n)
+            return self.trace_sim(tree, cfg, seed, cap=n, fish=fish)
         rec = buf[:n * 7].reshape(n, 7)
         return sim[0], rec[:, 0].astype(np.uint32), np.ascontiguousarray(rec[:, 1:])
 
-    def trace_medians(self, tree, cfgs, seeds):
+    def trace_medians(self, tree, cfgs, seeds, fish=False):
         """score(tree, seeds[k], {cfgs[k]}, trace=true) for k = 0.. on one tree -> (sims, use counts,
         medians[n_leaves, 6]) of the P^2 estimators MemoryRange::track feeds."""
         L = self.lib
@@ -221,7 +221,7 @@ class Oracle(_ScoreLib):
         L.remy_oracle_p2_init.argtypes = [_PTR]
         L.remy_oracle_p2_median.argtypes = [_PTR]
         L.remy_oracle_p2_median.restype = C.c_double
-        L.remy_oracle_trace_medians.argtypes = [C.POINTER(FlatTreeC), _PTR, _PTR, C.c_uint32, _PTR, _PTR, _PTR]
+        L.remy_oracle_trace_medians_kind.argtypes = [C.POINTER(FlatTreeC), _PTR, _PTR, C.c_uint32, C.c_int, _PTR, _PTR, _PTR]
         cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
         nl = tree.n_leaves
@@ -230,7 +230,7 @@ class Oracle(_ScoreLib):
             L.remy_oracle_p2_init(acc.ctypes.data + i * sz)
         sims = np.zeros(len(cfgs), dtype=sim_result_dtype)
         counts = np.zeros(nl, dtype=np.uint32)
-        L.remy_oracle_trace_medians(tree.byref(), _ptr(cfgs), _ptr(seeds), len(cfgs), _ptr(sims), _ptr(counts), _ptr(acc))
+        L.remy_oracle_trace_medians_kind(tree.byref(), _ptr(cfgs), _ptr(seeds), len(cfgs), int(fish), _ptr(sims), _ptr(counts), _ptr(acc))
         med = np.array([L.remy_oracle_p2_median(acc.ctypes.data + i * sz) for i in range(nl * NUM_AXES)]).reshape(nl, NUM_AXES)
         return sims, counts, med
 
@@ -309,10 +309,10 @@ class Device(_ScoreLib):
         except RuntimeError as e:
             raise RuntimeError(f"{e}: {self.last_error()}")
 
-    def score_trace(self, tree, cfgs, seeds):
-        """remy_b200_score_trace -> (sims, senders, use counts, [(leaf[n], values[n, words - 1]) per config])."""
+    def score_trace(self, tree, cfgs, seeds, fish=False):
+        """remy_b200_score_trace[_fish] -> (sims, senders, use counts, [(leaf[n], values[n, words - 1]) per config])."""
         sink_t = C.CFUNCTYPE(C.c_int, _PTR, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint32)
-        f = self.lib.remy_b200_score_trace
+        f = self.lib.remy_b200_score_trace_fish if fish else self.lib.remy_b200_score_trace
         f.restype = C.c_int
         f.argtypes = [C.POINTER(FlatTreeC), _PTR, _PTR, C.c_uint32, C.c_uint32, _PTR, _PTR, _PTR, sink_t, _PTR]
         cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)

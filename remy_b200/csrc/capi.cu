@@ -121,7 +121,7 @@ size_t smem_bytes(const RemyBatch *b, uint32_t n_max, bool with_tree)
 
 const void *kernel_fn(const RemyBatch *b)
 {
-  if (b->trace) return (const void *)remy_sim_kernel<true, true>;
+  if (b->trace) return b->fish ? (const void *)remy_sim_kernel<true, true, true> : (const void *)remy_sim_kernel<true, true>;
   if (b->fish) return b->want_counts ? (const void *)remy_sim_kernel<true, false, true> : (const void *)remy_sim_kernel<false, false, true>;
   return b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
 }
@@ -205,7 +205,8 @@ int launch(RemyBatch *b, const Scratch &s, size_t smem, bool tree_in_smem, const
 {
   CU(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
   const KernelArgs a = make_args(b, s, tree_in_smem, order, n_work, counter);
-  if (b->trace) remy_sim_kernel<true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  if (b->trace && b->fish) remy_sim_kernel<true, true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else if (b->trace) remy_sim_kernel<true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->fish && b->want_counts) remy_sim_kernel<true, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->fish) remy_sim_kernel<false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
@@ -247,6 +248,7 @@ int remy_b200_init(int device)
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_device = device; g_sms = prop.multiProcessorCount;
   g_err.clear();
@@ -502,17 +504,41 @@ int remy_b200_score_batch_fish(const RemyFlatTree *tree,
 }
 
 /* ---- trace == true scoring ------------------------------------------------------------ */
+static int score_trace_impl(const RemyFlatTree *tree,
+                            const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                            uint32_t sender_stride,
+                            RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
+                            RemyTraceSink sink, void *user, bool fish);
+
 int remy_b200_score_trace(const RemyFlatTree *tree,
                           const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
                           uint32_t sender_stride,
                           RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
                           RemyTraceSink sink, void *user)
 {
+  return score_trace_impl(tree, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders, out_use_counts, sink, user, false);
+}
+
+int remy_b200_score_trace_fish(const RemyFlatTree *tree,
+                               const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                               uint32_t sender_stride,
+                               RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
+                               RemyTraceSink sink, void *user)
+{
+  return score_trace_impl(tree, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders, out_use_counts, sink, user, true);
+}
+
+static int score_trace_impl(const RemyFlatTree *tree,
+                            const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                            uint32_t sender_stride,
+                            RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts,
+                            RemyTraceSink sink, void *user, bool fish)
+{
   if (!out_sims && n_cfgs) return fail(REMY_EINVAL, "out_sims is NULL");
   if (!sink) return fail(REMY_EINVAL, "sink is NULL");
   /* 1. counting run: scores, use counts, and the number of lookups of every simulation */
   RemyBatch *b = nullptr;
-  int rc = create_impl(tree, nullptr, 1, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, 1, 1, &b);
+  int rc = create_impl(tree, nullptr, 1, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, 1, 1, &b, fish);
   if (rc) return rc;
   std::vector<uint64_t> lookups(n_cfgs);
   uint32_t words = b->trace_words;
@@ -550,7 +576,7 @@ int remy_b200_score_trace(const RemyFlatTree *tree,
     while (g1 < n_cfgs && (g1 == g0 || (recs + lookups[g1]) * rec_bytes <= budget)) { offs.push_back(recs); recs += lookups[g1]; g1++; }
     if (recs * rec_bytes > budget && recs * rec_bytes > ((uint64_t)64 << 30)) { rc = fail(REMY_ENOMEM, "trace of one simulation exceeds the log budget"); break; }
     RemyBatch *g = nullptr;
-    rc = create_impl(tree, nullptr, 1, cfgs + g0, seeds + g0, g1 - g0, sender_stride, 0, 1, 2, &g);
+    rc = create_impl(tree, nullptr, 1, cfgs + g0, seeds + g0, g1 - g0, sender_stride, 0, 1, 2, &g, fish);
     if (rc) break;
     {
       std::lock_guard<std::mutex> lk(g_mu);

@@ -724,6 +724,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
      * no deadline is due and nothing changed: next_send stays valid) ---- */
     if (mail || (!half && maybe_sends)) {
       uint32_t ready = 0, ns_sender = 0xFFFFFFFFu;
+      uint32_t first_send = 0; /* Fish that looked their lambda up in this tick's send (trace) */
       double ns = DBL_MAX;
       uint32_t om = open_mask;
       while (om) {
@@ -753,6 +754,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
               const uint32_t leaf = find_leaf(T, zero, err);
               if (err) break;
               if (COUNT) cnt[leaf]++;
+              if (TRACE) { c->leaf = leaf; first_send |= 1u << s; } /* (its stored Memory is the all-zero one of the reset) */
               isend = (leaf == ov_leaf) ? A.cands[cand].intersend : T.leaves[leaf].intersend;
             }
             for (uint32_t b = 0; b < FISH_BATCH; b++, seq++) { /* Link::accept (link.hh:26-34) for each packet of the batch */
@@ -793,6 +795,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         }
       }
       next_send = ns;
+      /* trace of a Fish tick: per sender, in the shuffled order, the ack's lookup or (never both:
+       * an ack sets lambda) the first send's lookup on the all-zero Memory of the reset */
+      if (TRACE && FISH) track_senders(acked, first_send);
       if (ns_sender != 0xFFFFFFFFu) prefetch_line(&sendst[ns_sender]); /* what its transmission will read */
     }
 

@@ -8,6 +8,8 @@
 #include <functional>
 #include <iostream>
 #include <stdexcept>
+#include <ctime>
+#include <unistd.h>
 
 namespace remy_b200 {
 
@@ -217,7 +219,6 @@ static void check_fish_sim(const RemySimResult &r)
 Evaluator<FinTree>::Outcome Evaluator<FinTree>::score(FinTree &run_fins, unsigned int prng_seed, const std::vector<NetConfig> &configs,
                                                       bool trace, unsigned int ticks_to_run)
 { /* src/evaluator.cc:105-132, one seed per config like Evaluator<WhiskerTree>::score here */
-  if (trace) throw std::runtime_error("Evaluator<FinTree>::score: trace == true is not supported for Fish yet");
   const FlatTree ft = flatten(run_fins);
   const RemyFlatTree tree = ft.c();
   std::vector<RemyNetConfig> cfgs;
@@ -227,7 +228,20 @@ Evaluator<FinTree>::Outcome Evaluator<FinTree>::score(FinTree &run_fins, unsigne
   std::vector<RemySimResult> sims(cfgs.size());
   std::vector<RemySenderResult> snd(cfgs.size() * (size_t)stride);
   std::vector<uint32_t> counts(ft.leaves.size());
-  if (remy_b200_score_batch_fish(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride, sims.data(), snd.data(), counts.data()))
+  if (trace) { /* Fish(run_fins, seed, trace) (src/evaluator.cc:122): every lookup also feeds the fin's running medians */
+    struct Ctx { std::vector<const MemoryRange *> doms; uint32_t mask; } ctx;
+    std::vector<const Fin *> lv;
+    static_cast<const FinTree &>(run_fins).leaves(lv);
+    for (const Fin *f : lv) ctx.doms.push_back(&f->domain());
+    ctx.mask = 0;
+    for (const auto &nd : ft.nodes) ctx.mask |= nd.axis_mask;
+    auto feed = [](void *user, uint32_t, const uint64_t *rec, uint64_t n, uint32_t words) -> int {
+      Ctx *c = static_cast<Ctx *>(user);
+      return feed_trace_records(c->doms, c->mask, rec, n, words);
+    };
+    if (remy_b200_score_trace_fish(&tree, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride, sims.data(), snd.data(), counts.data(), feed, &ctx))
+      throw std::runtime_error(std::string("remy_b200_score_trace_fish: ") + remy_b200_last_error());
+  } else if (remy_b200_score_batch_fish(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride, sims.data(), snd.data(), counts.data()))
     throw std::runtime_error(std::string("remy_b200_score_batch_fish: ") + remy_b200_last_error());
   Outcome out;
   for (size_t k = 0; k < cfgs.size(); k++) {
@@ -329,6 +343,74 @@ double FinImprover::improve(Fin &action_to_improve)
   }
   std::cout << "Chose " << action_to_improve.str() << std::endl;
   return score_to_beat_;
+}
+
+/* ------------------------------------------------------------ FishBreeder -- */
+FishBreeder::FishBreeder(const BreederOptions &o, unsigned int seed) : _options(o), _seed_state(0)
+{
+  const unsigned int s = seed ? seed : (unsigned int)(time(NULL) ^ getpid());
+  _seed_state = s % 2147483647u;
+  if (_seed_state == 0) _seed_state = 1;
+}
+unsigned int FishBreeder::next_seed()
+{
+  _seed_state = (uint32_t)(((uint64_t)_seed_state * 16807u) % 2147483647u);
+  return _seed_state;
+}
+void FishBreeder::apply_best_split(FinTree &tree, unsigned int generation)
+{ /* Breeder<FinTree>::apply_best_split, src/breeder.cc:15-41 (without the fork's stray assert(false)) */
+  const Evaluator<FinTree> eval(_options.config_range, next_seed());
+  auto outcome(eval.score(tree, true));
+  while (1) {
+    const Fin *my_action = outcome.used_actions.most_used(generation);
+    if (!my_action) throw std::runtime_error("apply_best_split: no fin was used (reference assert, breeder.cc:25)");
+    FinTree bisected_action(*my_action, true);
+    if (bisected_action.num_children() == 1) {
+      printf("Got unbisectable whisker! %s\n", my_action->str().c_str());
+      Fin mutable_action(*my_action);
+      mutable_action.promote(generation + 1);
+      if (!outcome.used_actions.replace(mutable_action)) throw std::runtime_error("apply_best_split: replace failed (reference assert, breeder.cc:33)");
+      continue;
+    }
+    printf("Bisecting === %s === into === %s ===\n", my_action->str().c_str(), bisected_action.str().c_str());
+    if (!tree.replace(*my_action, bisected_action)) throw std::runtime_error("apply_best_split: replace failed (reference assert, breeder.cc:38)");
+    break;
+  }
+}
+Evaluator<FinTree>::Outcome FishBreeder::improve(FinTree &fins)
+{ /* src/fishbreeder.cc:7-72 */
+  FinTree input_fintree(fins);
+  fins.reset_generation();
+  unsigned int generation = 0;
+  while (generation < 5) {
+    const Evaluator<FinTree> eval(_options.config_range, next_seed());
+    auto outcome(eval.score(fins));
+    const Fin *most_used_fin_ptr = outcome.used_actions.most_used(generation);
+    if (!most_used_fin_ptr) { generation++; fins.promote(generation); continue; }
+    FinImprover improver(eval, fins, outcome.score);
+    Fin fin_to_improve = *most_used_fin_ptr;
+    double score_to_beat = outcome.score;
+    while (1) {
+      const double new_score = improver.improve(fin_to_improve);
+      if (new_score < score_to_beat) throw std::runtime_error("FishBreeder: score decreased (reference assert, fishbreeder.cc:41)");
+      if (new_score == score_to_beat) { std::cerr << "Ending search." << std::endl; break; }
+      std::cerr << "Score jumps from " << score_to_beat << " to " << new_score << std::endl;
+      score_to_beat = new_score;
+    }
+    candidates_scored += improver.candidates_scored; batches += improver.batches;
+    fin_to_improve.demote(generation + 1);
+    if (!fins.replace(fin_to_improve)) throw std::runtime_error("FishBreeder: replace failed (reference assert, fishbreeder.cc:55)");
+  }
+  apply_best_split(fins, generation);
+  const Evaluator<FinTree> eval2(_options.config_range, next_seed());
+  const auto new_score = eval2.score(fins, false, 10);
+  const auto old_score = eval2.score(input_fintree, false, 10);
+  if (old_score.score >= new_score.score) {
+    fprintf(stderr, "Regression, old=%f, new=%f\n", old_score.score, new_score.score);
+    fins = input_fintree;
+    return old_score;
+  }
+  return new_score;
 }
 
 } // namespace remy_b200

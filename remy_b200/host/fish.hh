@@ -4,9 +4,7 @@
  *   Fin                     reference src/fin.hh:11-57, src/fin.cc
  *   FinTree                 reference src/fintree.hh, src/fintree.cc
  *   Evaluator<FinTree>      reference src/evaluator.hh:14-56, src/evaluator.cc:105-132,148-160
- *   FinImprover             reference src/fishbreeder.hh:6-14 over ActionImprover (src/breeder.cc:43-150)
- * Not mirrored yet: FishBreeder::improve's apply_best_split (it needs trace == true scoring of Fish
- * lookups, which the device path does not log yet).
+ *   FinImprover, FishBreeder reference src/fishbreeder.{hh,cc} over ActionImprover / Breeder (src/breeder.cc:15-150)
  */
 #ifndef REMY_HOST_FISH_HH
 #define REMY_HOST_FISH_HH
@@ -14,6 +12,7 @@
 #include <unordered_map>
 
 #include "remy.hh"
+#include "breeder.hh"
 
 namespace remy_b200 {
 
@@ -109,6 +108,17 @@ public:
   FinImprover(const Evaluator<FinTree> &evaluator, const FinTree &fish, double score_to_beat)
     : eval_(evaluator), tree_(fish), score_to_beat_(score_to_beat) {}
   double improve(Fin &action_to_improve);                   /* src/breeder.cc:116-150 */
+  size_t candidates_scored = 0, batches = 0;
+};
+
+class FishBreeder {
+  BreederOptions _options;
+  uint32_t _seed_state; /* stands in for global_PRNG() (src/random.cc:7-11): one draw per Evaluator */
+  unsigned int next_seed();
+public:
+  explicit FishBreeder(const BreederOptions &options, unsigned int seed = 0);
+  Evaluator<FinTree>::Outcome improve(FinTree &fins);                 /* src/fishbreeder.cc:7-72 */
+  void apply_best_split(FinTree &fins, unsigned int generation);      /* Breeder<FinTree>::apply_best_split */
   size_t candidates_scored = 0, batches = 0;
 };
 

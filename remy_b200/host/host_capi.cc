@@ -274,6 +274,49 @@ long remy_host_improve_fin(void *h, const void *range_bytes, size_t range_size, 
     return calls;)
 }
 
+/* Evaluator<FinTree>::score(tree, seed, configs, trace = true, ticks) over explicit NetConfigs — needs a GPU */
+int remy_host_fish_score_trace(void *h, const RemyNetConfig *cfgs, uint32_t n_cfgs, unsigned int prng_seed, double *score)
+{
+  GUARD(
+    FinTree &t = *(FinTree *)h;
+    std::vector<NetConfig> configs;
+    for (uint32_t k = 0; k < n_cfgs; k++) {
+      NetConfig c; c.mean_on_duration = cfgs[k].mean_on_duration; c.mean_off_duration = cfgs[k].mean_off_duration;
+      c.num_senders = cfgs[k].num_senders; c.link_ppt = cfgs[k].link_ppt; c.delay = cfgs[k].delay;
+      c.buffer_size = cfgs[k].buffer_size; c.stochastic_loss_rate = cfgs[k].stochastic_loss_rate;
+      configs.push_back(c);
+    }
+    const auto out = Evaluator<FinTree>::score(t, prng_seed, configs, true, n_cfgs ? (unsigned int)cfgs[0].simulation_ticks : 0);
+    *score = out.score;
+    return 0;)
+}
+int remy_host_fintree_medians(void *h, double *out, uint32_t n_leaves)
+{
+  GUARD(
+    std::vector<const Fin *> lv; ((FinTree *)h)->leaves(lv);
+    for (size_t l = 0; l < lv.size() && l < n_leaves; l++)
+      for (unsigned a = 0; a < Memory::datasize; a++) out[l * Memory::datasize + a] = lv[l]->domain()._acc[a].median();
+    return 0;)
+}
+/* Breeder<FinTree>::apply_best_split through FishBreeder — needs a GPU */
+int remy_host_fish_apply_best_split(void *h, const void *range_bytes, size_t range_size, unsigned int seed, unsigned int generation)
+{
+  GUARD(
+    BreederOptions o; o.config_range = ConfigRange::parse(range_bytes, range_size);
+    FishBreeder b(o, seed);
+    b.apply_best_split(*(FinTree *)h, generation);
+    return 0;)
+}
+/* FishBreeder::improve; the tree behind `h` is updated in place — needs a GPU */
+int remy_host_fishbreeder_improve(void *h, const void *range_bytes, size_t range_size, unsigned int seed, double *score)
+{
+  GUARD(
+    BreederOptions o; o.config_range = ConfigRange::parse(range_bytes, range_size);
+    FishBreeder b(o, seed);
+    *score = b.improve(*(FinTree *)h).score;
+    return 0;)
+}
+
 /* ---- trace == true ---- */
 
 /* P2Median fed with `n` samples — no GPU needed */

@@ -549,7 +549,7 @@ namespace {
  * returned (src/whiskertree.cc:55-57), in the order the device reports them (config by config,
  * and within a config in the reference's call order). */
 struct TrackSink {
-  std::vector<Whisker *> leaves;
+  std::vector<const MemoryRange *> leaves; /* the domain of every leaf, depth-first */
   std::vector<int> axes; /* axis of record word 1, 2, ... */
   std::vector<uint32_t> leaf_axes; /* active-axis mask of every leaf */
   /* One estimator per (leaf, axis), each fed in record order: the pairs are independent of each
@@ -563,7 +563,7 @@ struct TrackSink {
       for (size_t k = 0; k < na; k++) {
         if (!(mask & (1u << axes[k])) || (l * na + k) % parts != part) continue;
         double v; memcpy(&v, &rec[1 + k], sizeof v);
-        leaves[l]->domain()._acc[axes[k]](v);
+        leaves[l]->_acc[axes[k]](v);
       }
     }
   }
@@ -581,22 +581,37 @@ struct TrackSink {
     return 0;
   }
 };
-TrackSink make_sink(WhiskerTree &tree)
+TrackSink make_sink(const std::vector<const MemoryRange *> &leaf_domains, uint32_t all_axes_mask)
 {
   TrackSink sink;
-  tree.leaves(sink.leaves);
-  uint32_t mask = 0;
-  for (const Whisker *w : sink.leaves) { sink.leaf_axes.push_back(w->domain().axis_mask()); mask |= w->domain().axis_mask(); }
-  std::vector<const WhiskerTree *> stack { &tree }; /* interior nodes count too: the union over ALL nodes, as in the device layout */
-  while (!stack.empty()) { const WhiskerTree *t = stack.back(); stack.pop_back(); mask |= t->_domain.axis_mask(); for (const auto &c : t->_children) stack.push_back(&c); }
-  for (int a = 0; a < REMY_NUM_AXES; a++) if (mask & (1u << a)) sink.axes.push_back(a);
+  sink.leaves = leaf_domains;
+  for (const MemoryRange *d : leaf_domains) sink.leaf_axes.push_back(d->axis_mask());
+  for (int a = 0; a < REMY_NUM_AXES; a++) if (all_axes_mask & (1u << a)) sink.axes.push_back(a);
   return sink;
+}
+TrackSink make_sink(WhiskerTree &tree)
+{
+  std::vector<const Whisker *> lv;
+  static_cast<const WhiskerTree &>(tree).leaves(lv);
+  std::vector<const MemoryRange *> doms;
+  for (const Whisker *w : lv) doms.push_back(&w->domain());
+  uint32_t mask = 0;
+  std::vector<const WhiskerTree *> stack { &tree }; /* the union over ALL nodes, as in the device layout */
+  while (!stack.empty()) { const WhiskerTree *t = stack.back(); stack.pop_back(); mask |= t->_domain.axis_mask(); for (const auto &c : t->_children) stack.push_back(&c); }
+  return make_sink(doms, mask);
 }
 } // namespace
 
 int feed_trace_records(WhiskerTree &tree, const uint64_t *records, uint64_t n_records, uint32_t words_per_record)
 {
   TrackSink sink = make_sink(tree);
+  return TrackSink::feed(&sink, 0, records, n_records, words_per_record);
+}
+
+int feed_trace_records(const std::vector<const MemoryRange *> &leaf_domains, uint32_t all_axes_mask,
+                       const uint64_t *records, uint64_t n_records, uint32_t words_per_record)
+{
+  TrackSink sink = make_sink(leaf_domains, all_axes_mask);
   return TrackSink::feed(&sink, 0, records, n_records, words_per_record);
 }
 

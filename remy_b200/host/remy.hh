@@ -194,6 +194,9 @@ private:
  * name: MemoryRange::track for every record, in order (several host threads, one per subset of the
  * independent (leaf, axis) estimators).  Returns non-zero on a malformed record. */
 int feed_trace_records(WhiskerTree &tree, const uint64_t *records, uint64_t n_records, uint32_t words_per_record);
+/* the same for any tree type: the leaves' domains depth-first + the union of the axes active anywhere in the tree */
+int feed_trace_records(const std::vector<const MemoryRange *> &leaf_domains, uint32_t all_axes_mask,
+                       const uint64_t *records, uint64_t n_records, uint32_t words_per_record);
 
 /* POD view of a WhiskerTree for the C ABI. */
 struct FlatTree {

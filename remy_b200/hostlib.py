@@ -53,6 +53,10 @@ class HostLib:
         L.remy_host_fish_score.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_double, C.POINTER(C.c_double), _V, C.c_uint32]
         L.remy_host_improve_fin.restype = C.c_long
         L.remy_host_improve_fin.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint32, _V]
+        L.remy_host_fish_score_trace.argtypes = [_V, _V, C.c_uint32, C.c_uint, C.POINTER(C.c_double)]
+        L.remy_host_fintree_medians.argtypes = [_V, _V, C.c_uint32]
+        L.remy_host_fish_apply_best_split.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.c_uint]
+        L.remy_host_fishbreeder_improve.argtypes = [_V, C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_double)]
         L.remy_host_p2_median.restype = C.c_double
         L.remy_host_p2_median.argtypes = [_V, C.c_size_t]
         L.remy_host_track.argtypes = [_V, C.c_uint32, _V, C.c_size_t]
@@ -173,6 +177,26 @@ class HostFinTree:
                                                 counts.ctypes.data, len(counts))
         self.host._check(rc == 0)
         return score.value, counts
+
+    def score_trace(self, cfgs, prng_seed):
+        """Evaluator<FinTree>::score(tree, seed, configs, trace=true, ticks) (needs a GPU)."""
+        cfgs = np.ascontiguousarray(cfgs, dtype=abi.net_config_dtype)
+        score = C.c_double(0)
+        self.host._check(self.host.lib.remy_host_fish_score_trace(self.h, cfgs.ctypes.data, len(cfgs), prng_seed, C.byref(score)) == 0)
+        return score.value
+
+    def medians(self, n_leaves):
+        out = np.zeros((n_leaves, abi.NUM_AXES))
+        self.host._check(self.host.lib.remy_host_fintree_medians(self.h, out.ctypes.data, n_leaves) == 0)
+        return out
+
+    def apply_best_split(self, range_bytes, seed, generation=0):
+        self.host._check(self.host.lib.remy_host_fish_apply_best_split(self.h, range_bytes, len(range_bytes), seed, generation) == 0)
+
+    def fishbreeder_improve(self, range_bytes, seed):
+        score = C.c_double(0)
+        self.host._check(self.host.lib.remy_host_fishbreeder_improve(self.h, range_bytes, len(range_bytes), seed, C.byref(score)) == 0)
+        return score.value
 
     def improve_fin(self, range_bytes, prng_seed, leaf):
         """FinImprover::improve until the score stops rising -> (calls, score, lambda, candidates, batches)."""

@@ -94,9 +94,20 @@ static int score_batch_kind(const RemyFlatTree *tree,
  * trace_words = 1 + popcount(axes) words each, written back to back into `log` (capacity
  * cap_records records; returns REMY_ENOMEM if it does not fit).  Two runs per simulation, like
  * the library: a counting run, then the run that writes. */
+static int trace_kind(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                      RemySimResult *out_sims, uint32_t *out_use_counts,
+                      uint64_t *log, uint64_t cap_records, uint64_t *out_lookups, uint32_t *out_words, int fish);
 extern "C" int remy_emu_trace(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
                               RemySimResult *out_sims, uint32_t *out_use_counts,
                               uint64_t *log, uint64_t cap_records, uint64_t *out_lookups, uint32_t *out_words)
+{ return trace_kind(tree, cfgs, seeds, n_cfgs, out_sims, out_use_counts, log, cap_records, out_lookups, out_words, 0); }
+extern "C" int remy_emu_trace_fish(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                   RemySimResult *out_sims, uint32_t *out_use_counts,
+                                   uint64_t *log, uint64_t cap_records, uint64_t *out_lookups, uint32_t *out_words)
+{ return trace_kind(tree, cfgs, seeds, n_cfgs, out_sims, out_use_counts, log, cap_records, out_lookups, out_words, 1); }
+static int trace_kind(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                      RemySimResult *out_sims, uint32_t *out_use_counts,
+                      uint64_t *log, uint64_t cap_records, uint64_t *out_lookups, uint32_t *out_words, int fish)
 {
   PreparedTree pt;
   if (!prepare_tree(tree, pt).empty()) return REMY_EINVAL;
@@ -128,7 +139,8 @@ extern "C" int remy_emu_trace(const RemyFlatTree *tree, const RemyNetConfig *cfg
         A.out_use_counts = phase == 1 ? out_use_counts : scratch_counts.data();
         A.trace_log = phase == 1 ? log : nullptr; A.trace_off = offs.data(); A.out_lookups = out_lookups; A.trace_words = words;
         TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
-        run_sim<true, true>(A, T, k, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        if (fish) run_sim<true, true, true>(A, T, k, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        else run_sim<true, true>(A, T, k, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
         if (!(out_sims[k].error & REMY_ERR_LINK_OVERFLOW) || cap >= (1u << 24)) break;
         cap *= 16;
       }

@@ -190,3 +190,71 @@ def test_gpu_host_fish_evaluator_and_improver(host, device, oracle):
             break
     assert calls == want_calls and got_lambda == lam and abs(got_score - best) <= 1e-9 * abs(best)
     assert batches <= 2 * calls
+
+
+def test_kernel_fish_trace_equals_oracle(built, oracle):
+    """trace == true for Fish on the CPU build of the kernel: per sender, in the shuffled order, the ack's
+    lookup or the first send's lookup on the all-zero Memory of the reset; one rtt_diff value per record."""
+    from helpers import ROOT
+    emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "libremy_emu.so"))
+    emu.remy_emu_trace_fish.argtypes = [C.POINTER(abi.FlatTreeC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(9)
+    cfgs = random_configs(rng, 24, max_ticks=5000)
+    seeds = rng.integers(1, 2**31 - 2, len(cfgs)).astype(np.uint32)
+    for tree in (abi.fin_tree([5.0]), abi.fin_tree([5.0, 1.0, 0.3], [2.0, 20.0])):
+        n = len(cfgs)
+        sims = np.zeros(n, dtype=abi.sim_result_dtype)
+        counts = np.zeros(tree.n_leaves, dtype=np.uint32)
+        cap = 2_000_000
+        log = np.zeros(cap * 2, dtype=np.uint64)
+        looks = np.zeros(n, dtype=np.uint64)
+        words = C.c_uint32()
+        rc = emu.remy_emu_trace_fish(tree.byref(), cfgs.ctypes.data, seeds.ctypes.data, n, sims.ctypes.data, counts.ctypes.data,
+                                     log.ctypes.data, cap, looks.ctypes.data, C.byref(words))
+        assert rc == 0 and words.value == 2
+        off = 0
+        for k in range(n):
+            _, leaf, mem = oracle.trace_sim(tree, cfgs[k], seeds[k], fish=True)
+            assert len(leaf) == looks[k], k
+            rec = log[off * 2:(off + len(leaf)) * 2].reshape(-1, 2)
+            assert (rec[:, 0] == leaf).all() and rec[:, 1].tobytes() == np.ascontiguousarray(mem[:, 4]).tobytes(), k
+            off += len(leaf)
+        assert off == counts.sum() > 100000
+
+
+@pytest.mark.gpu
+def test_gpu_fish_trace_and_split(host, device, oracle):
+    """remy_b200_score_trace_fish against the oracle's lookup log; Evaluator<FinTree>::score(trace = true) leaves the
+    oracle's running medians on every fin; Breeder<FinTree>::apply_best_split cuts the most used fin at its median."""
+    from remy_b200 import hostlib, workloads
+    rng = np.random.default_rng(19)
+    cfgs = random_configs(rng, 32, max_ticks=5000)
+    seeds = rng.integers(1, 2**31 - 2, len(cfgs)).astype(np.uint32)
+    flat = abi.fin_tree([5.0, 1.0, 0.3], [2.0, 20.0])
+    sims, snd, counts, recs = device.score_trace(flat, cfgs, seeds, fish=True)
+    plain = device.score_fish(flat, cfgs, seeds, want_use_counts=True)
+    assert sims.tobytes() == plain[0].tobytes() and (counts == plain[2]).all()
+    for k in range(len(cfgs)):
+        _, leaf, mem = oracle.trace_sim(flat, cfgs[k], seeds[k], fish=True)
+        gl, gv = recs[k]
+        assert len(gl) == len(leaf) and (gl == leaf).all() and gv.tobytes() == np.ascontiguousarray(mem[:, 4:5]).tobytes(), k
+    # host: medians after a traced score, then the split
+    raw = hostlib.encode_config_range(link=(1, 2, 0.5), rtt=(100, 150, 50), nsrc=(1, 9, 4), buf=(50, 50, 0),
+                                      off=(0, 0, 0), on=(1e9, 1e9, 0), ticks=20000)
+    hc, _ = host.expand(raw)
+    breeder_seed = 77
+    eval_seed = (breeder_seed * 16807) % 2147483647
+    hs = workloads.seeds_for(eval_seed, len(hc))
+    _, ocounts, omed = oracle.trace_medians(flat, hc, hs, fish=True)
+    tree = host.fintree_from_flat(flat)
+    tree.score_trace(hc, eval_seed)
+    assert tree.medians(flat.n_leaves)[:, 4].tobytes() == omed[:, 4].tobytes()
+    tree2 = host.fintree_from_flat(flat)
+    tree2.apply_best_split(raw, breeder_seed, 0)
+    got = tree2.flatten()
+    top = int(np.argmax(np.where(ocounts >= ocounts.max(), np.arange(len(ocounts)), -1)))   # most_used: the last of the maxima
+    assert got.n_leaves == flat.n_leaves + 1
+    lo, hi = [0.0, 2.0, 20.0][top], [2.0, 20.0, 163840.0][top]
+    cuts = sorted(set(float(n["lower"][4]) for n in got.nodes) | set(float(n["upper"][4]) for n in got.nodes))
+    assert float(omed[top, 4]) in cuts and lo < float(omed[top, 4]) < hi
