@@ -3,7 +3,8 @@
  * on the GPU through Evaluator<WhiskerTree> (remy.hh).  scripts/plot.py and tests/ (.pm) of the
  * reference parse this output ("sender: [tp=..., del=...]", src/sender-runner.cc:27-43).
  *
- * Reference arguments: if= nsrc= link= rtt= on= off= buf= sloss=   (sender=poisson is out of scope)
+ * Reference arguments: sender=poisson (Fish over a FinTree, src/sender-runner.cc:59-68,80-87,138-141)
+ *   if= nsrc= link= rtt= on= off= buf= sloss=
  * Extensions (the reference has none of these): seed=N (default: time ^ pid, src/random.cc:9),
  *   ticks=N (default 1000000, src/sender-runner.cc:57), cf=FILE (a config/ .cfg ConfigRange[Unicorn]
  *   file, mapped as in SURVEY.md Appendix A: every *.low; on <= 0 -> 5000 ms), dev=N.
@@ -17,6 +18,7 @@
 #include <sstream>
 #include <string>
 
+#include "fish.hh"
 #include "pbwire.hh"
 #include "remy.hh"
 
@@ -65,13 +67,14 @@ static string debug_string(const uint8_t *data, size_t size, const FieldName *sc
   return out;
 }
 
-static void print_tree(const string &raw)
+static void print_tree(const string &raw, bool fin_tree)
 {
   pb::Reader rd(raw); pb::Field f;
   string config, optimizer; bool has_config = false, has_opt = false;
+  const uint32_t f_config = fin_tree ? 93 : 4, f_opt = fin_tree ? 94 : 5; /* protobufs/dna.proto:10-12,24-26 */
   while (rd.next(f)) {
-    if (f.number == 4 && f.wire_type == 2) { config = debug_string(f.data, f.size, CONFIG_RANGE, 0); has_config = true; }
-    if (f.number == 5 && f.wire_type == 2) { optimizer = debug_string(f.data, f.size, OPT_SETTINGS, 0); has_opt = true; }
+    if (f.number == f_config && f.wire_type == 2) { config = debug_string(f.data, f.size, CONFIG_RANGE, 0); has_config = true; }
+    if (f.number == f_opt && f.wire_type == 2) { optimizer = debug_string(f.data, f.size, OPT_SETTINGS, 0); has_opt = true; }
   }
   if (has_config) printf("Prior assumptions:\n%s\n\n", config.c_str());
   if (has_opt) printf("Remy optimization settings:\n%s\n\n", optimizer.c_str());
@@ -80,6 +83,8 @@ static void print_tree(const string &raw)
 int main(int argc, char *argv[])
 {
   WhiskerTree whiskers;
+  FinTree fins;
+  bool is_poisson = false;
   unsigned int num_senders = 2;
   double link_ppt = 1.0, delay = 100.0, mean_on_duration = 5000.0, mean_off_duration = 5000.0;
   double buffer_size = numeric_limits<unsigned int>::max();
@@ -90,8 +95,8 @@ int main(int argc, char *argv[])
   for (int i = 1; i < argc; i++) {
     string arg(argv[i]);
     if (arg.substr(0, 7) == "sender=" && arg.substr(7) == "poisson") {
-      fprintf(stderr, "sender=poisson (Fish/FinTree) is outside the scope of remy-b200\n");
-      return 1;
+      is_poisson = true;
+      fprintf(stderr, "Running poisson sender\n");
     }
   }
   /* key=value arguments: the numeric ones are table-driven; each echoes the reference's stderr line */
@@ -120,9 +125,9 @@ int main(int argc, char *argv[])
     if (numeric) continue;
     if (key == "if=") {
       const string raw = slurp(val);
-      try { whiskers = WhiskerTree::parse(raw.data(), raw.size()); }
+      try { if (is_poisson) fins = FinTree::parse(raw.data(), raw.size()); else whiskers = WhiskerTree::parse(raw.data(), raw.size()); }
       catch (const exception &e) { fprintf(stderr, "Could not parse %s.\n", val.c_str()); return 1; }
-      print_tree(raw);
+      print_tree(raw, is_poisson);
     } else if (key == "cf=") {
       const string raw = slurp(val);
       const ConfigRange r = ConfigRange::parse(raw.data(), raw.size());
@@ -154,13 +159,11 @@ int main(int argc, char *argv[])
   configuration_range.simulation_ticks = simulation_ticks;
 
   if (remy_b200_init(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
-  try {
-    Evaluator<WhiskerTree> eval(configuration_range, seed);
-    auto outcome = eval.score(whiskers, false, 10);
-    /* parse_outcome (src/sender-runner.cc:27-43) */
-    printf("score = %f\n", outcome.score);
+  /* parse_outcome (src/sender-runner.cc:27-43) */
+  auto parse_outcome = [](double score, const vector<pair<NetConfig, vector<pair<double, double>>>> &tds, const string &rules) {
+    printf("score = %f\n", score);
     double norm_score = 0;
-    for (auto &run : outcome.throughputs_delays) {
+    for (auto &run : tds) {
       printf("===\nconfig: %s\n", run.first.str().c_str());
       for (auto &x : run.second) {
         printf("sender: [tp=%f, del=%f]\n", x.first / run.first.link_ppt, x.second / run.first.delay);
@@ -168,7 +171,18 @@ int main(int argc, char *argv[])
       }
     }
     printf("normalized_score = %f\n", norm_score);
-    printf("Rules: %s\n", outcome.used_actions.str().c_str());
+    printf("Rules: %s\n", rules.c_str());
+  };
+  try {
+    if (is_poisson) {
+      Evaluator<FinTree> eval(configuration_range, seed);
+      auto outcome = eval.score(fins, false, 10);
+      parse_outcome(outcome.score, outcome.throughputs_delays, outcome.used_actions.str());
+    } else {
+      Evaluator<WhiskerTree> eval(configuration_range, seed);
+      auto outcome = eval.score(whiskers, false, 10);
+      parse_outcome(outcome.score, outcome.throughputs_delays, outcome.used_actions.str());
+    }
   } catch (const exception &e) {
     fprintf(stderr, "%s\n", e.what());
     return 1;

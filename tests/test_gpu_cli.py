@@ -95,3 +95,31 @@ def test_remy_cli_writes_checkpoints(built, device, tmp_path):
     sr = subprocess.run([os.path.join(ROOT, "remy_b200", "host", "sender-runner"), f"if={of}.0", "nsrc=2", "link=1", "rtt=100",
                          "seed=1", "ticks=2000"], capture_output=True, text=True, timeout=300)
     assert sr.returncode == 0 and sr.stdout.startswith("Prior assumptions:\nlink_packets_per_ms {\n  low: 1\n  high: 2\n  incr: 1\n}")
+
+
+def test_sender_runner_poisson(built, device, oracle, tmp_path):
+    """`sender-runner sender=poisson if=<FinTree>` (src/sender-runner.cc:59-68,80-87,138-141): Fish senders over a
+    FinTree file, digits pinned against the oracle's Fish."""
+    built.build_host()
+    host = hostlib.HostLib()
+    flat = abi.fin_tree([5.0, 1.0, 0.3], [2.0, 20.0])
+    path = tmp_path / "fins.dna"
+    path.write_bytes(host.fintree_from_flat(flat).serialize())
+    exe = os.path.join(ROOT, "remy_b200", "host", "sender-runner")
+    out = subprocess.run([exe, "sender=poisson", f"if={path}", "nsrc=3", "link=1.5", "rtt=120", "on=2000", "off=1000", "buf=40",
+                          "seed=11", "ticks=4000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "Running poisson sender" in out.stderr
+    cfg = abi.make_configs([dict(link_ppt=1.5, delay=120, num_senders=3, mean_on_duration=2000, mean_off_duration=1000,
+                                 buffer_size=40, simulation_ticks=40000.0)])
+    sims, snd, _ = oracle.score_fish(flat, cfg, np.array([11], dtype=np.uint32))
+    assert ("score = %f" % sims[0]["utility"]) in out.stdout
+    senders = re.findall(r"sender: \[tp=([0-9.eE+-]+), del=([0-9.eE+-]+)\]", out.stdout)
+    want = []
+    for s in range(3):
+        r = snd[0][s]
+        tp = 0.0 if r["tick_share_sending"] == 0 else r["packets_received"] / r["tick_share_sending"]
+        dl = 0.0 if r["packets_received"] == 0 else r["total_delay"] / r["packets_received"]
+        want.append(("%f" % (tp / 1.5), "%f" % (dl / 120.0)))
+    assert senders == want
+    assert "Rules: [{(lo=< rttd=0.000000 >, hi=< rttd=2.000000 >)} gen=0 usage=" in out.stdout and "(lambda=5.000000)]" in out.stdout
