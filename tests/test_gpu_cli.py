@@ -123,3 +123,39 @@ def test_sender_runner_poisson(built, device, oracle, tmp_path):
         want.append(("%f" % (tp / 1.5), "%f" % (dl / 120.0)))
     assert senders == want
     assert "Rules: [{(lo=< rttd=0.000000 >, hi=< rttd=2.000000 >)} gen=0 usage=" in out.stdout and "(lambda=5.000000)]" in out.stdout
+
+
+def test_remy_poisson_cli_writes_checkpoints(built, device, tmp_path):
+    """`remy-poisson cf=... of=... runs=1` (src/remy-poisson.cc): banner, per-config report and a checkpoint `<of>.0`
+    that is a RemyBuffers.FinTree carrying config, optimizer and configvector, readable by python-protobuf and by
+    `sender-runner sender=poisson`."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import pb_schema
+    built.build_host()
+    cfg_path = tmp_path / "range.cfg"
+    cfg_path.write_bytes(hostlib.encode_config_range(link=(1, 2, 1), rtt=(100, 100, 0), nsrc=(2, 4, 2), buf=(40, 40, 0),
+                                                     off=(0, 0, 0), on=(1e9, 1e9, 0), ticks=3000))
+    exe = os.path.join(ROOT, "remy_b200", "host", "remy-poisson")
+    of = tmp_path / "fish"
+    out = subprocess.run([exe, f"cf={cfg_path}", f"of={of}", "runs=1", "seed=5"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Evaluator simulations will run for 3000 ticks" in out.stdout
+    assert "Optimizing for link packets_per_ms in [1.000000, 2.000000]" in out.stdout
+    assert "Optimizing for buffer_size in [40.000000, 40.000000]" in out.stdout
+    assert re.search(r"^run = 0, score = -?[0-9.]+$", out.stdout, re.M) and "Alternatives: lambda" in out.stdout
+    assert out.stdout.count("config: mean_on=1000000000.000000") == 4 and out.stdout.count("sender: [tp=") == 2 * (2 + 4)
+    raw = (tmp_path / "fish.0").read_bytes()
+    msg = pb_schema.classes()["FinTree"]()
+    msg.ParseFromString(raw)
+    assert msg.SerializeToString() == raw
+    assert msg.config.simulation_ticks == 3000 and msg.config.num_senders.high == 4
+    assert getattr(msg.optimizer, "lambda").max_value == 30 and len(msg.configvector.config) == 4
+    leaves = [msg.leaf] if msg.HasField("leaf") else [c.leaf for c in msg.children]
+    assert len(leaves) in (1, 2) and "Bisecting ===" in out.stdout          # one signal (rtt_diff): a split makes two fins
+    for leaf in leaves:
+        assert 0.01 <= getattr(leaf, "lambda") <= 30
+    sr = subprocess.run([os.path.join(ROOT, "remy_b200", "host", "sender-runner"), "sender=poisson", f"if={of}.0", "nsrc=2", "link=1",
+                         "rtt=100", "seed=1", "ticks=1000"], capture_output=True, text=True, timeout=300)
+    assert sr.returncode == 0 and sr.stdout.startswith("Prior assumptions:\nlink_packets_per_ms {\n  low: 1\n  high: 2\n  incr: 1\n}")
+    assert "lambda {" in sr.stdout and "score = " in sr.stdout
