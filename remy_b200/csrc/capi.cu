@@ -3,7 +3,7 @@
  *
  * Host side of the boundary only: argument checking, flattening the tree into
  * the device layout (with the per-node cell tables), the config-sorted work
- * list split into passes by sender count, scratch sizing, kernel launches on
+ * list (one launch per batch; optionally a launch per sender-count bucket), scratch sizing, kernel launches on
  * the library's streams, and the bounded re-run of simulations whose link
  * queue outgrew the ring they were given.  There is no CPU implementation of
  * the simulator in this library: without a CUDA device every entry point
@@ -310,7 +310,7 @@ static int create_impl(const RemyFlatTree *tree,
   if (!pt.cuts.empty()) CU(cudaMemcpyAsync(b->cuts.p, pt.cuts.data(), pt.cuts.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   if (!pt.table.empty()) CU(cudaMemcpyAsync(b->table.p, pt.table.data(), pt.table.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, g_stream));
 
-  /* ---- configs: ring sizes, config-sorted order, passes by sender count ---- */
+  /* ---- configs: ring sizes, config-sorted order, launches ("passes": one by default) ---- */
   /* One launch over one cost-sorted list (largest sender counts first).  Cutting the batch into a
    * launch per sender-count bucket (REMY_B200_SINGLE_PASS=0) buys nothing - residency is bound by
    * registers, not by the per-sender shared memory - and costs a drain per launch: a block leaves
@@ -392,7 +392,7 @@ int remy_b200_batch_run(RemyBatch *b, float *kernel_ms)
   if (b->want_counts) CU(cudaMemsetAsync(b->out_counts.p, 0, b->out_counts.n * sizeof(uint32_t), g_stream));
   CU(cudaEventRecord(b->ev0, g_stream));
   if (b->n_sims) {
-    /* the passes run concurrently on their own streams, largest sender counts first; as a
+    /* (with REMY_B200_SINGLE_PASS=0 there are several:) the passes run concurrently on their own streams, largest sender counts first; as a
      * pass drains, the next one's blocks take over the freed SM resources */
     for (size_t i = 0; i < b->passes.size(); i++) {
       Pass &ps = *b->passes[i];

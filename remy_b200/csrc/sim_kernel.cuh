@@ -29,6 +29,14 @@
  *   std::deque<Packet> x3, vector<vector<Packet>> two per-slot rings in HBM; the
  *     (link.hh, delay.hh, receiver.hh)            Receiver mailbox is a window of the
  *                                                 delay ring, never copied
+ *   one Network::tick per loop iteration          the tick that reads a delivered packet
+ *     (network.cc:73-84)                          runs in the pass that delivered it
+ *                                                 ("fused tick", see run_sim); the loop has
+ *                                                 ONE exit, at its top, so that the warp
+ *                                                 re-converges behind every phase
+ *
+ * Template parameters: COUNT keeps per-leaf use counts, TRACE logs every lookup for the host's
+ * running medians (remy_b200_score_trace), FISH swaps the Rat for the Fish sender (FinTree).
  *
  * Every floating-point expression that feeds control flow keeps the
  * reference's association and is compiled without FMA contraction
