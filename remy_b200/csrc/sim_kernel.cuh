@@ -859,11 +859,17 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
 }
 
 constexpr int SIM_BLOCK = 128;
+#ifndef REMY_MIN_BLOCKS_PER_SM
+/* Three resident blocks per SM = 168 registers per thread and no spills.  Four (128 registers, 44 B of
+ * spills and re-reads of per-simulation constants) gave 33 % more warps but measured 10 % slower on the
+ * final kernel (8.47 vs 9.34 G event ticks/s, 102 400 simulations x 3e4 ticks); two (255 registers) 18 % slower. */
+#define REMY_MIN_BLOCKS_PER_SM 3
+#endif
 
 #ifndef REMY_HOST_EMU
 
 template <bool COUNT, bool TRACE = false, bool FISH = false>
-__global__ void __launch_bounds__(SIM_BLOCK, 4) remy_sim_kernel(const KernelArgs A)
+__global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   /* layout: [inc_buf: INC_BUF*B doubles][hot_send: n_max*B doubles][tree, if staged] */
