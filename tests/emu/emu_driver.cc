@@ -62,7 +62,7 @@ static int score_batch_kind(const RemyFlatTree *tree,
   if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * (size_t)n_cands * tree->n_leaves);
   uint32_t cap = plan.link_cap;
   std::vector<uint32_t> todo = plan.order;
-  for (int round = 0; round < 5 && !todo.empty(); round++) {
+  for (int round = 0; round < 8 && !todo.empty(); round++) { /* rings grow 16x per round up to 2^24 entries, like the library's re-runs */
     std::vector<LinkEnt> lring(cap);
     KernelArgs A;
     memset(&A, 0, sizeof A);
@@ -85,7 +85,7 @@ static int score_batch_kind(const RemyFlatTree *tree,
     }
     todo.swap(redo);
     if (cap >= (1u << 24)) break;
-    cap *= 16;
+    cap = (uint32_t)std::min<uint64_t>((uint64_t)cap * 16, 1u << 24);
   }
   return 0;
 }
