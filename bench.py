@@ -336,7 +336,8 @@ def main():
                                      "masks in registers/shared memory, so its real DRAM traffic (`traffic`, ncu dram bytes of the step's one "
                                      "simulation launch, profiles/traffic.json) is ~9x smaller and `frac` can exceed 1; `dram_gbs` is the HBM "
                                      "bandwidth actually used. The path is latency/issue bound (ncu --set full, profiles/r01_ncu_full_final.txt: "
-                                     "30% issue slots, 14.4/32 lanes, long-scoreboard 6.0 cycles per issued instruction), not HBM bound."},
+                                     "30% issue slots, 14.4/32 lanes, long-scoreboard 6.0 cycles per issued instruction; captured with 4 resident "
+                                     "blocks per SM, the library now builds with 3), not HBM bound."},
                 "cpu_baseline": cpu,
                 "event_ticks_per_sec": ticks_all * args.steps / secs, "sims_per_sec": sims_all * args.steps / secs,
                 "evals_per_sec": sims_all / 800.0 * args.steps / secs, "score_sum": score_all}
