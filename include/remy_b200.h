@@ -119,12 +119,23 @@ typedef struct RemySenderResult {
 /* Bind the calling process to CUDA device `device` (one process per GPU) and
  * create the library's stream.  Returns 0, or a negative REMY_E* code. */
 int remy_b200_init(int device);
+/* Bind the calling process to SEVERAL devices (devices == NULL or n_devices <= 0: all visible ones).
+ * Every batch created afterwards is partitioned over them: the cost-sorted list of (candidate, config)
+ * simulations is dealt round-robin to the devices, each runs its share on its own stream, and the
+ * results are gathered into the caller's arrays under the caller's simulation ids - what the
+ * reference does with one std::async thread per candidate on the cores of one machine
+ * (src/breeder.cc:53-77).  Results do not depend on the number of devices (per-simulation results are
+ * returned, not partial sums).  trace == true scoring always runs on the first device of the list.
+ * Replaces any earlier binding. */
+int remy_b200_init_devices(const int *devices, int n_devices);
+/* Number of devices bound by the last successful init (0 before any). */
+int remy_b200_device_count(void);
 void remy_b200_shutdown(void);
 /* Human-readable description of the last failure on this thread ("" if none). */
 const char *remy_b200_last_error(void);
 /* ABI version of this header; bumped on any layout change. */
 uint32_t remy_b200_abi_version(void);
-#define REMY_B200_ABI_VERSION 1u
+#define REMY_B200_ABI_VERSION 2u
 
 #define REMY_EINVAL   (-1) /* bad argument */
 #define REMY_ENODEV   (-2) /* no CUDA device / init not called */
@@ -175,8 +186,13 @@ int remy_b200_batch_run(RemyBatch *batch, float *kernel_ms);
 int remy_b200_batch_fetch(RemyBatch *batch, RemySimResult *out_sims,
                           RemySenderResult *out_senders, uint32_t *out_use_counts);
 void remy_b200_batch_destroy(RemyBatch *batch);
-/* Number of kernel launches performed by the last remy_b200_batch_run. */
+/* Number of kernel launches performed by the last remy_b200_batch_run (all devices). */
 uint32_t remy_b200_batch_launches(const RemyBatch *batch);
+/* Number of simulations the last run had to repeat with larger link rings (see REMY_ERR_LINK_OVERFLOW:
+ * hidden from the caller as long as the queue fits 2^24 packets). */
+uint32_t remy_b200_batch_rerun(const RemyBatch *batch);
+/* Number of devices the batch was partitioned over. */
+uint32_t remy_b200_batch_devices(const RemyBatch *batch);
 
 /* ---- second sender family: Fish over a FinTree ----------------------------- *
  * Replaces: Evaluator<FinTree>::score (src/evaluator.cc:105-132): the same network with Fish
@@ -194,6 +210,13 @@ int remy_b200_score_batch_fish(const RemyFlatTree *tree,
                                RemySimResult *out_sims,
                                RemySenderResult *out_senders,
                                uint32_t *out_use_counts);
+
+/* Staged form of the above (run / fetch / destroy as for remy_b200_batch_create). */
+int remy_b200_batch_create_fish(const RemyFlatTree *tree,
+                                const RemyLeafOverride *cands, uint32_t n_cands,
+                                const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                uint32_t sender_stride, int want_senders, int want_use_counts,
+                                RemyBatch **out_batch);
 
 /* ---- trace == true scoring ------------------------------------------------ *
  * Replaces: Evaluator<WhiskerTree>::score(tree, trace = true) (src/evaluator.cc:77-103 with

@@ -278,6 +278,8 @@ class Device(_ScoreLib):
     is no CPU fallback."""
 
     def __init__(self, device=0, path=None):
+        """device: a CUDA device index, or a list of them (None = all visible): every batch is then
+        partitioned over those devices (remy_b200_init_devices)."""
         path = path or os.path.join(REPO_ROOT, "remy_b200", "csrc", "libremy_b200.so")
         if not os.path.exists(path):
             raise RuntimeError(f"CUDA extension not built: {path} (run python -c 'import __graft_entry__ as g; g.build()')")
@@ -285,9 +287,30 @@ class Device(_ScoreLib):
         self.lib.remy_b200_last_error.restype = C.c_char_p
         self.lib.remy_b200_init.argtypes = [C.c_int]
         self.lib.remy_b200_abi_version.restype = C.c_uint32
-        rc = self.lib.remy_b200_init(device)
+        self.abi_version = self.lib.remy_b200_abi_version()
+        if self.abi_version < 2:   # an older build of the library (A/B tooling): one device, no staged Fish batches
+            if not isinstance(device, int):
+                raise RuntimeError(f"{path}: ABI v{self.abi_version} binds one device only")
+            rc = self.lib.remy_b200_init(device)
+            if rc != 0:
+                raise RuntimeError(f"remy_b200_init({device}) failed with {rc}: {self.last_error()}")
+            self.n_devices = 1
+            self._bind_batch_api()
+            return
+        self.lib.remy_b200_init_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
+        if isinstance(device, int):
+            rc = self.lib.remy_b200_init(device)
+        elif device is None:
+            rc = self.lib.remy_b200_init_devices(None, 0)
+        else:
+            arr = (C.c_int * len(device))(*device)
+            rc = self.lib.remy_b200_init_devices(arr, len(device))
         if rc != 0:
             raise RuntimeError(f"remy_b200_init({device}) failed with {rc}: {self.last_error()}")
+        self.n_devices = self.lib.remy_b200_device_count()
+        self._bind_batch_api()
+
+    def _bind_batch_api(self):
         self.lib.remy_b200_batch_create.restype = C.c_int
         self.lib.remy_b200_batch_create.argtypes = [C.POINTER(FlatTreeC), _PTR, C.c_uint32, _PTR, _PTR, C.c_uint32,
                                                     C.c_uint32, C.c_int, C.c_int, C.POINTER(_PTR)]
@@ -296,8 +319,12 @@ class Device(_ScoreLib):
         self.lib.remy_b200_batch_fetch.restype = C.c_int
         self.lib.remy_b200_batch_fetch.argtypes = [_PTR, _PTR, _PTR, _PTR]
         self.lib.remy_b200_batch_destroy.argtypes = [_PTR]
-        self.lib.remy_b200_batch_launches.restype = C.c_uint32
-        self.lib.remy_b200_batch_launches.argtypes = [_PTR]
+        for name in ("remy_b200_batch_launches", "remy_b200_batch_rerun", "remy_b200_batch_devices")[:3 if self.abi_version >= 2 else 1]:
+            getattr(self.lib, name).restype = C.c_uint32
+            getattr(self.lib, name).argtypes = [_PTR]
+        if self.abi_version >= 2:
+            self.lib.remy_b200_batch_create_fish.restype = C.c_int
+            self.lib.remy_b200_batch_create_fish.argtypes = self.lib.remy_b200_batch_create.argtypes
 
     def last_error(self):
         return self.lib.remy_b200_last_error().decode()
@@ -341,14 +368,14 @@ class Device(_ScoreLib):
             out.append((a[:, 0].astype(np.uint32), np.ascontiguousarray(a[:, 1:]).view(np.float64)))
         return sims, senders, counts, out
 
-    def create_batch(self, tree, cfgs, seeds, cands=None, want_senders=False, want_use_counts=False):
-        return DeviceBatch(self, tree, cfgs, seeds, cands, want_senders, want_use_counts)
+    def create_batch(self, tree, cfgs, seeds, cands=None, want_senders=False, want_use_counts=False, fish=False):
+        return DeviceBatch(self, tree, cfgs, seeds, cands, want_senders, want_use_counts, fish)
 
 
 class DeviceBatch:
     """Staged scoring: inputs stay resident in HBM between runs."""
 
-    def __init__(self, dev, tree, cfgs, seeds, cands, want_senders, want_use_counts):
+    def __init__(self, dev, tree, cfgs, seeds, cands, want_senders, want_use_counts, fish=False):
         self.dev = dev
         self.tree = tree
         self.cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
@@ -360,7 +387,8 @@ class DeviceBatch:
         self.want_senders = want_senders
         self.want_use_counts = want_use_counts
         h = _PTR()
-        rc = dev.lib.remy_b200_batch_create(tree.byref(), _ptr(self.cands), self.n_cands, _ptr(self.cfgs),
+        create = dev.lib.remy_b200_batch_create_fish if fish else dev.lib.remy_b200_batch_create
+        rc = create(tree.byref(), _ptr(self.cands), self.n_cands, _ptr(self.cfgs),
                                             _ptr(self.seeds), len(self.cfgs), self.stride,
                                             int(want_senders), int(want_use_counts), C.byref(h))
         if rc != 0:
@@ -376,6 +404,13 @@ class DeviceBatch:
 
     def launches(self):
         return self.dev.lib.remy_b200_batch_launches(self.h)
+
+    def rerun(self):
+        """simulations the last run repeated with larger link rings"""
+        return self.dev.lib.remy_b200_batch_rerun(self.h)
+
+    def devices(self):
+        return self.dev.lib.remy_b200_batch_devices(self.h)
 
     def fetch(self):
         sims = np.zeros(self.n, dtype=sim_result_dtype)

@@ -55,6 +55,8 @@
 #define REMY_NOINLINE __attribute__((noinline))
 #else
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #define REMY_NOINLINE __noinline__
 #endif
 #include "../../include/remy_b200.h"
@@ -64,7 +66,16 @@
 namespace remy {
 
 constexpr uint32_t LCG_M = 2147483647u;
-constexpr uint32_t INC_BUF = 8; /* buffered sending-time increments per simulation (shared memory) */
+constexpr uint32_t INC_BUF = 16;  /* buffered sending-time increments per simulation (shared memory) */
+#ifndef REMY_CHAIN
+#define REMY_CHAIN 1 /* chained ticks (see run_sim); 0 = one reference tick per pass of the event loop */
+#endif
+#ifndef REMY_EARLY_COLD
+#define REMY_EARLY_COLD 0
+#endif
+#ifndef REMY_SD_REPS
+#define REMY_SD_REPS 2 /* times the transmission + link phases are gone through per pass */
+#endif
 
 struct KernelArgs {
   /* tree (global copies; staged into shared memory when it fits) */
@@ -78,6 +89,8 @@ struct KernelArgs {
   const RemyNetConfig *cfgs;     /* [n_cfgs] */
   const uint32_t *seeds;         /* [n_cfgs] */
   const uint32_t *order;         /* [n_work] simulation ids, cost-sorted */
+  const uint32_t *sim_map;       /* nullptr, or [n_sims]: the (candidate, config) index each local simulation id stands for
+                                  * (a batch partitioned over several devices: ids, work list and outputs are per device) */
   uint32_t n_cfgs, n_work;
   uint32_t *work_counter;
   /* per-slot scratch */
@@ -110,12 +123,18 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #endif
 }
-__device__ __forceinline__ void prefetch_line(const void *p)
+/* Maximum of v over the lanes of the warp that are executing this call together.  Lanes of a warp
+ * run different simulations and leave the event loop at different times, so there is no point at
+ * which a full-warp mask is known; cooperative groups' coalesced_threads() is the defined way to
+ * name "the lanes that are here" and to reduce over exactly them.  The result only steers WHEN the
+ * buffered sending-time increments are applied, never what is computed. */
+__device__ __forceinline__ uint32_t warp_max_here(uint32_t v)
 {
 #ifdef REMY_HOST_EMU
-  (void)p;
+  return v;
 #else
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+  return cooperative_groups::reduce(g, v, cooperative_groups::greater<uint32_t>());
 #endif
 }
 
@@ -215,6 +234,22 @@ __device__ REMY_NOINLINE void shuffle_materialise(uint32_t x, uint32_t n, uint8_
   }
 }
 
+/* dt / k for a small integer k (1..32 senders that are on) and dt >= 0, correctly rounded, without
+ * the division routine; inv_k = RN(1/k).  With q0 = RN(dt inv_k), the residual r = dt - k q0 is exact
+ * in one FMA (it is a multiple of ulp(q0) of magnitude < 2^7 ulp), and q0 + r inv_k differs from dt/k
+ * by a relative 2^-105; dt/k with k <= 32 is either a double or at least ulp/64 away from the nearest
+ * rounding boundary (k = 2^p o with o odd: a quotient that terminates in binary has o | mantissa and
+ * fits 53 bits, so no quotient is an exact midpoint), hence the final rounding gives RN(dt/k): the
+ * value of the reference's `(tickno - _internal_tick) / num_sending` (src/sendergang.cc:169-171).
+ * Checked against the hardware division for every k on 10^8 random and edge-case dt by
+ * tests/test_kernel_emu.py::test_small_divisor_division. */
+__device__ __forceinline__ double div_small_int(double dt, double k, double inv_k)
+{
+  const double q0 = __dmul_rn(dt, inv_k);
+  const double r = __fma_rn(-q0, k, dt);
+  return __fma_rn(r, inv_k, q0);
+}
+
 /* ------------------------------------------------------------- whiskers --- */
 struct TreeView {
   const Bounds *bounds;  const DevNodeMeta *meta; const DevLeaf *leaves;
@@ -306,7 +341,8 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         SendState *sendst,                  /* [n_max] mirror of the send fields of `cold` */
                         SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
 {
-  const uint32_t cand = sim / A.n_cfgs, cfg_i = sim - cand * A.n_cfgs;
+  const uint32_t pair = A.sim_map ? A.sim_map[sim] : sim;
+  const uint32_t cand = pair / A.n_cfgs, cfg_i = pair - cand * A.n_cfgs;
   const RemyNetConfig cfg = A.cfgs[cfg_i];
   RemySimResult res;
   res.utility = 0; res.last_tick = 0; res.event_ticks = 0; res.packets_sent = 0; res.packets_received = 0;
@@ -379,54 +415,59 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   }
   if (COUNT) for (uint32_t l = 0; l < A.n_leaves; l++) cnt[l] = 0;
 
-  double t = 0.0, t_prev = 0.0;
+  double t = 0.0;
   uint32_t on_mask = 0, open_mask = 0, zero_mask = 0;
   double next_send = DBL_MAX;          /* min of hot_send over open senders */
   bool pending = false;                /* Link::_pending_packet non-empty */
   double pend_release = 0, pend_sent = 0; uint32_t pend_seq = 0, pend_src = 0;
   uint32_t lhead = 0, ltail = 0;       /* Link::_buffer ring */
   uint32_t dcons = 0, ddeliv = 0, dtail = 0; /* delay ring: [dcons,ddeliv) = Receiver mailbox, [ddeliv,dtail) in flight */
-  /* the oldest in-flight delay entry and the (single) delivered-but-unread one are kept in
-   * registers: the ring is only read when an entry becomes the head */
+  /* the oldest in-flight delay entry is kept in registers: the ring is only read when an entry
+   * becomes the head */
   double dhead_release = DBL_MAX, dh_sent = 0; uint32_t dh_seq = 0, dh_src = 0;
   /* ... and so is the entry behind it (valid when dtail - ddeliv >= 2), so that the HBM read of
    * a delay-ring entry is issued a whole service time before its first use */
   double dn_release = 0, dn_sent = 0; uint32_t dn_seq = 0, dn_src = 0;
+  /* ... and the packet the latest Delay::tick delivered (the first entry of the mailbox), which the
+   * senders read in the next tick */
+  double m_sent = 0; uint32_t m_seq = 0, m_src = 0;
   uint64_t iters = 0;
   /* Sending time is accumulated exactly as the reference does (one rounded addition of
    * dt/k per sender per tick, sendergang.cc:163-173), but the additions are deferred: the
    * per-tick increments are identical for every sender that is on, so up to INC_BUF of them
    * are kept in shared memory and applied, in order, to each such sender at once.  The set
-   * of senders cannot change while increments are buffered (a switch flushes first). */
-  uint32_t ninc = 0, acc_mask = 0;
+   * of senders that are on cannot change while increments are buffered (a switch flushes first,
+   * and the increment of a switch tick itself is applied at once). */
+  uint32_t ninc = 0;
+  double inv_on = 0; /* correctly rounded 1 / (number of senders that are on) */
   auto flush_share = [&]() {
-    uint32_t am = acc_mask;
-    /* always INC_BUF additions per sender, from registers: unused slots hold +0.0, and v + 0.0 == v
-     * exactly for the non-negative sums kept here */
-    for (uint32_t k = ninc; k < INC_BUF; k++) inc_buf[k * HS] = 0.0;
-    double inc[INC_BUF];
-#pragma unroll
-    for (uint32_t k = 0; k < INC_BUF; k++) inc[k] = inc_buf[k * HS];
+    /* Four senders at a time: their sums are requested together (one memory latency per group instead of
+     * one per sender), and the four addition chains - each strictly in order, as the reference adds -
+     * interleave in the FP64 pipe.  The increments are read from shared memory once per group; padding up
+     * to a multiple of two holds +0.0 (v + 0.0 == v exactly for the non-negative sums kept here). */
+    const uint32_t kmax = (ninc + 1u) & ~1u;
+    if (ninc & 1u) inc_buf[ninc * HS] = 0.0;
+    uint32_t am = on_mask;
     while (am) {
-      const uint32_t s = __ffs(am) - 1; am &= am - 1;
-      double v = share[s];
-#pragma unroll
-      for (uint32_t k = 0; k < INC_BUF; k++) v = __dadd_rn(v, inc[k]);
-      share[s] = v;
+      const uint32_t s0 = __ffs(am) - 1; am &= am - 1;
+      const bool h1 = am != 0; const uint32_t s1 = h1 ? __ffs(am) - 1 : s0; am &= am - 1;
+      const bool h2 = am != 0; const uint32_t s2 = h2 ? __ffs(am) - 1 : s0; am &= am - 1;
+      const bool h3 = am != 0; const uint32_t s3 = h3 ? __ffs(am) - 1 : s0; am &= am - 1;
+      double v0 = share[s0], v1 = share[s1], v2 = share[s2], v3 = share[s3];
+      for (uint32_t k = 0; k < kmax; k += 2) {
+        const double i0 = inc_buf[k * HS], i1 = inc_buf[(k + 1) * HS];
+        v0 = __dadd_rn(__dadd_rn(v0, i0), i1); v1 = __dadd_rn(__dadd_rn(v1, i0), i1);
+        v2 = __dadd_rn(__dadd_rn(v2, i0), i1); v3 = __dadd_rn(__dadd_rn(v3, i0), i1);
+      }
+      share[s0] = v0;
+      if (h1) share[s1] = v1;
+      if (h2) share[s2] = v2;
+      if (h3) share[s3] = v3;
     }
     ninc = 0;
   };
+  auto share_of = [&](double dt, double k) { return div_small_int(dt, k, inv_on); };
 
-  /* One pass of this loop = one reference tick, or two when the tick delivers a packet: the tick
-   * that follows a delivery happens at the same time t (Receiver::next_event_time, receiver.hh:34-37)
-   * and consists of nothing but the shuffle's draws, the ack and the sends it releases, so it is run
-   * in the same pass, right behind the delivery ("fused tick").  Every lane of a warp then reaches
-   * the expensive ack code once per pass instead of once every other pass.  For that the link and
-   * delay phases of a tick come BEFORE the (single) ack/send code in the pass, which is only
-   * equivalent if the tick itself has nothing to send; a tick that may send AND has a departure or
-   * a delivery due is therefore split over two passes (`half`): senders first, link + delay (and
-   * the fused tick) in the next pass. */
-  bool half = false, maybe_sends = false;
   uint32_t prng_before_shuffle = prng;
   /* trace: the lookups of run_senders happen sender by sender in the shuffled order
    * (sendergang.cc:83-86 -> TimeSwitchedSender::tick, :190-205): the ack's lookup, then
@@ -461,204 +502,176 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     }
     if (TRACE) track_senders(acked, zero_mask & on_mask);
   };
+  /* A chained tick: the sender phase (up to the transmissions) of a reference tick at time t2 > t in
+   * which no switch is due and no mail is waiting - run_senders' shuffle draws (sendergang.cc:75-82)
+   * and the sending-time increment (sendergang.cc:163-173).  See the loop below. */
+  auto chain_ok = [&]() { return REMY_CHAIN && !err && t < duration && dcons == ddeliv && ninc < INC_BUF; };
+  auto begin_chained_tick = [&](double t2) {
+    iters++;
+    prng_before_shuffle = prng;
+    prng = shuffle_skip(prng, n);
+    zero_window_lookups(0);
+    if (on_mask) { inc_buf[ninc * HS] = share_of(__dsub_rn(t2, t), (double)__popc(on_mask)); ninc++; }
+    t = t2;
+  };
 
-  /* The loop is left at ONE place, its top, and nowhere inside a conditional block (an error only
+  /* One pass of this loop = up to FOUR reference ticks.  The phases of a tick come in the reference's
+   * order - senders (switches, shuffle, acks, transmissions), link, delay (network.cc:54-61) - and each
+   * of the three expensive ones exists ONCE in the loop body.  A pass starts with whatever tick is next
+   * (network.cc:75-78), the only place where switches and mail are handled.  In front of the
+   * transmission, link and delay phases there is a "chain point":
+   * if the tick so far is over (nothing else is due at its time) and the NEXT reference tick needs
+   * nothing but that phase and the ones behind it - a pacing deadline in front of the transmissions,
+   * a departure in front of the link phase, a delivery in front of the delay phase, and no switch -
+   * time advances right there (begin_chained_tick) and the pass goes on as that tick.  On a busy link
+   * every packet costs one transmission, one departure, one delivery and one ack tick; when they come
+   * in that order all four share a pass, and every lane of a warp reaches every phase in most passes,
+   * instead of each phase being run for the third of the lanes whose tick happens to need it.
+   * Coincident events need no special case: a tick that transmits, has a departure AND a delivery runs
+   * its phases in order in one pass.
+   *
+   * The loop is left at ONE place, its top, and nowhere inside a conditional block (an error only
    * sets `err` and lets the pass run out): early exits from inside divergent regions keep the
    * compiler from re-converging the warp behind them, and every phase below then runs once per
    * group of lanes instead of once per pass. */
+  /* the send state of ONE sender is held in registers across passes: the sender acked last, or else the
+   * one whose pacing deadline comes next (requested at the end of the transmission phase, a pass or more
+   * before its transmission reads it) */
+  uint32_t ak_s = 0xFFFFFFFFu, ak_seq = 0; int32_t ak_lim = 0; double ak_isend = 0;
   for (;;) {
-    bool run_link = true;
-    /* ---- next event (network.cc:75-78); the Receiver never holds mail here (it is read in the
-     * pass that delivers it), except when the run ends on a delivery ---- */
-    double tn = fmax(t, fmin(min_switch, next_send)); /* SenderGang::next_event_time */
+    /* ---- next event (network.cc:75-78) ---- */
+    const bool mail = dcons != ddeliv;                  /* Receiver::next_event_time: now (receiver.hh:34-37) */
+    double tn = fmax(t, fmin(min_switch, next_send));   /* SenderGang::next_event_time */
     if (pending) tn = fmin(tn, pend_release);           /* Link::next_event_time */
     if (ddeliv != dtail) tn = fmin(tn, dhead_release);  /* Delay::next_event_time */
+    if (mail) tn = t;
+    if (err || !(t < duration)) break;
+    if (tn > duration) { t = tn; break; } /* Network::_tickno keeps the overshooting time */
+    const double t_old = t;
+    t = tn;
+    iters++;
+    const bool advanced = t > t_old;
+    bool maybe_sends = next_send <= t; /* a window or pacing deadline changed in this tick, or a deadline is due */
+
+    /* the buffered sending-time increments are applied when the buffer of ANY lane that is here could
+     * overflow in this pass (this tick and the chained ones): every such lane then flushes in the same
+     * pass; a switch needs the sums up to date */
     {
-      const bool ended = !half && !(t < duration);
-      const bool overshoot = !half && !ended && tn > duration; /* Network::_tickno keeps the overshooting time */
-      if (overshoot) t = tn;
-      if (err || ended || overshoot) break;
+      const bool sw = min_switch <= t;
+      const uint32_t fullest = warp_max_here(ninc);
+      constexpr uint32_t PER_PASS = REMY_CHAIN ? 2 + 2 * REMY_SD_REPS : 1; /* increments a pass can add */
+      if ((fullest + PER_PASS > INC_BUF || sw) && ninc) flush_share();
     }
-    if (!half) {
-      t = tn;
-      iters++;
-      const bool advanced = t > t_prev;
+
+    /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
+    if (min_switch <= t) {
+      maybe_sends = true;
+      ak_s = 0xFFFFFFFFu; /* (the switches rewrite send states) */
       uint32_t newly_on = 0;
-      bool sends_dirty = false; /* a window or pacing deadline changed in this tick */
-
-      /* ---- 1. switch_senders (sendergang.cc:39-45, 89-106) ---- */
-      if (min_switch <= t) {
-        sends_dirty = true;
-        flush_share();
-        const uint32_t k0 = __popc(on_mask);
-        double ms = DBL_MAX;
-        for (uint32_t s = 0; s < n && !err; s++) {
-          double nx = nsw[s];
-          if (nx <= t) {
-            if (nx != t) err |= REMY_ERR_ASSERT;
-            SenderCold c = cold[s];
-            bool sending = (on_mask >> s) & 1u;
-            double itick = t_prev;       /* SwitchedSender::internal_tick of a sender that was on */
-            double shr = share[s];
-            do {
-              if (sending) {             /* switch_off (sendergang.cc:151-161) */
-                if (t > itick) { shr = __dadd_rn(shr, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
-                sending = false;
-              } else {                   /* switch_on -> Rat::reset (rat.cc:34-48) */
-                sending = true;
-  #pragma unroll
-                for (int a = 0; a < NAX; a++) c.mem[a] = 0;
-                c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0;
-                c.last_send_time = 0;
-                c.largest_ack = (int32_t)(c.packets_sent - 1u);
-                if (FISH) {              /* Fish::reset (fish.cc:36-48): no lookup, lambda = 0 until the first send or ack */
-                  c.intersend = 0;
-                } else {
-                  const uint32_t leaf = find_leaf(T, c.mem, err);
-                  if (err) break;
-                  if (COUNT) cnt[leaf]++;
-                  track(leaf, c.mem);
-                  DevLeaf w = T.leaves[leaf];
-                  if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
-                  c.window = whisker_window(0, w.window_multiple, w.window_increment);
-                  c.intersend = w.intersend;
-                  c.leaf = leaf;
-                }
-                itick = t;
+      const uint32_t k0 = __popc(on_mask);
+      double ms = DBL_MAX;
+      for (uint32_t s = 0; s < n && !err; s++) {
+        double nx = nsw[s];
+        if (nx <= t) {
+          if (nx != t) err |= REMY_ERR_ASSERT;
+          SenderCold c = cold[s];
+          bool sending = (on_mask >> s) & 1u;
+          double itick = t_old;        /* SwitchedSender::internal_tick of a sender that was on */
+          double shr = share[s];
+          do {
+            if (sending) {             /* switch_off (sendergang.cc:151-161) */
+              if (t > itick) { shr = __dadd_rn(shr, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
+              sending = false;
+            } else {                   /* switch_on -> Rat::reset (rat.cc:34-48) */
+              sending = true;
+#pragma unroll
+              for (int a = 0; a < NAX; a++) c.mem[a] = 0;
+              c.last_tick_sent = 0; c.last_tick_received = 0; c.min_rtt = 0;
+              c.last_send_time = 0;
+              c.largest_ack = (int32_t)(c.packets_sent - 1u);
+              if (FISH) {              /* Fish::reset (fish.cc:36-48): no lookup, lambda = 0 until the first send or ack */
+                c.intersend = 0;
+              } else {
+                const uint32_t leaf = find_leaf(T, c.mem, err);
+                if (err) break;
+                if (COUNT) cnt[leaf]++;
+                track(leaf, c.mem);
+                DevLeaf w = T.leaves[leaf];
+                if (leaf == ov_leaf) { const RemyLeafOverride o = A.cands[cand]; w.window_multiple = o.window_multiple; w.intersend = o.intersend; w.window_increment = o.window_increment; }
+                c.window = whisker_window(0, w.window_multiple, w.window_increment);
+                c.intersend = w.intersend;
+                c.leaf = leaf;
               }
-              nx = __dadd_rn(nx, exp_sample(prng, __ddiv_rn(1.0, sending ? cfgp->mean_on_duration : cfgp->mean_off_duration)));
-            } while (nx <= t);
-            nsw[s] = nx;
-            cold[s] = c;
-            { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = FISH ? c.window : c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
-            share[s] = shr;
-            const uint32_t bit = 1u << s;
-            if (sending) {
-              on_mask |= bit;
-              if (itick == t) newly_on |= bit;
-              /* (a sender that is on after its switch tick was reset in it: a Fish then sends at once) */
-              const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
-              hot_send[s * HS] = FISH ? 0.0 : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
-              open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
-              if (COUNT && !FISH) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
-            } else {
-              on_mask &= ~bit; open_mask &= ~bit;
-              hot_send[s * HS] = DBL_MAX;
-              if (COUNT) zero_mask &= ~bit;
+              itick = t;
             }
+            nx = __dadd_rn(nx, exp_sample(prng, __ddiv_rn(1.0, sending ? cfgp->mean_on_duration : cfgp->mean_off_duration)));
+          } while (nx <= t);
+          nsw[s] = nx;
+          cold[s] = c;
+          { SendState ss; ss.packets_sent = c.packets_sent; ss.lim = FISH ? c.window : c.largest_ack + 1 + c.window; ss.intersend = c.intersend; sendst[s] = ss; }
+          share[s] = shr;
+          const uint32_t bit = 1u << s;
+          if (sending) {
+            on_mask |= bit;
+            if (itick == t) newly_on |= bit;
+            /* (a sender that is on after its switch tick was reset in it: a Fish then sends at once) */
+            const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
+            hot_send[s * HS] = FISH ? 0.0 : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
+            open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
+            if (COUNT && !FISH) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+          } else {
+            on_mask &= ~bit; open_mask &= ~bit;
+            hot_send[s * HS] = DBL_MAX;
+            if (COUNT) zero_mask &= ~bit;
           }
-          ms = fmin(ms, nx);
         }
-        min_switch = ms;
+        ms = fmin(ms, nx);
       }
+      min_switch = ms;
+      /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) of a switch tick: applied at once to the
+       * senders that were on before it and still are (nothing is buffered here: ninc == 0) ---- */
       const uint32_t k1 = __popc(on_mask);
-
-      /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
-      prng_before_shuffle = prng;
-      prng = shuffle_skip(prng, n);
-      zero_window_lookups(0);
-
-      /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) ---- */
+      if (k1) inv_on = __ddiv_rn(1.0, (double)k1);
       if (advanced) {
         uint32_t am = on_mask & ~newly_on;
         if (am) {
-          if (ninc && am != acc_mask) flush_share();
-          acc_mask = am;
-          inc_buf[ninc * HS] = __ddiv_rn(__dsub_rn(t, t_prev), (double)k1);
-          ninc++;
+          const double inc = share_of(__dsub_rn(t, t_old), (double)k1);
+          while (am) { const uint32_t s = __ffs(am) - 1; am &= am - 1; share[s] = __dadd_rn(share[s], inc); }
         }
       }
-      t_prev = t;
-      /* flush when the buffer of ANY lane that is here is full: every such lane then flushes in
-       * the same pass (at most INC_BUF increments are pending; a lane adds at most one per pass) */
-      {
-        const uint32_t fullest = __reduce_max_sync(__activemask(), ninc);
-        if (fullest >= INC_BUF) { if (ninc) flush_share(); }
-        else if (fullest == INC_BUF - 1 && ninc) { /* next pass flushes: start fetching the sums */
-          for (uint32_t s0 = 0; s0 < n; s0 += 16) prefetch_line(&share[s0]);
-        }
-      }
-
-      maybe_sends = sends_dirty || next_send <= t;
-      if (maybe_sends && ((pending && pend_release <= t) || (ddeliv != dtail && dhead_release <= t))) run_link = false;
+    } else if (advanced && on_mask) {
+      /* ---- 5. accumulate_sending_time_until, buffered ---- */
+      inc_buf[ninc * HS] = share_of(__dsub_rn(t, t_old), (double)__popc(on_mask));
+      ninc++;
     }
 
-    bool mail = false;
-    double m_sent = 0; uint32_t m_seq = 0, m_src = 0; /* the packet delivered in this pass (mail is read in the pass that delivers it) */
-    if (run_link) {
-      /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
-      if (pending && pend_release <= t) {
-        if (pend_release != t) err |= REMY_ERR_ASSERT;
-        bool lost;
-        if (lossy) lost = canonical(prng) < cfgp->stochastic_loss_rate; /* bernoulli (bits/random.h:3739-3750) */
-        else { prng = lcg_mul(prng, 282475249u); lost = false; } /* two draws, 16807^2 */
-        if (!lost) {
-          if (dtail - dcons >= A.delay_cap) err |= REMY_ERR_DELAY_OVERFLOW;
-          else {
-          DelayEnt e; e.release = __dadd_rn(t, delay); e.tick_sent = pend_sent; e.seq = pend_seq; e.src = pend_src; e.pad[0] = 0; e.pad[1] = 0;
-          dring[dtail & dmask] = e;
-          if (ddeliv == dtail) { /* it is the head of the delay line right away */
-            dhead_release = e.release; dh_sent = e.tick_sent; dh_seq = e.seq; dh_src = e.src;
-          } else if (dtail - ddeliv == 1) { /* ... or the entry right behind the head */
-            dn_release = e.release; dn_sent = e.tick_sent; dn_seq = e.seq; dn_src = e.src;
-          }
-          dtail++;
-          }
-        }
-        pending = false;
-      }
-      if (!pending && lhead != ltail) {
-        const LinkEnt e = lring[lhead & lmask]; lhead++;
-        if ((lhead & 7u) == 0 && (ltail - lhead) > 8) prefetch_line(&lring[(lhead + 8) & lmask]); /* next 128-byte line of the queue */
-        pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
-      }
-      /* ---- 7. Delay::tick (delay.hh:53-63) -> Receiver::accept ---- */
-      /* (not written as a loop over the register-held head: a loop's condition would wait for
-       * the ring read issued below, which exists precisely so that nothing waits for it) */
-      if (ddeliv != dtail && dhead_release <= t) {
-        if (dhead_release != t) err |= REMY_ERR_ASSERT;
-        /* Receiver::accept: the delivered packet's fields move to the mail registers */
-        m_sent = dh_sent; m_seq = dh_seq; m_src = dh_src;
-        ddeliv++;
-        if (ddeliv != dtail) {
-          dhead_release = dn_release; dh_sent = dn_sent; dh_seq = dn_seq; dh_src = dn_src;
-          if (dhead_release <= t) { /* rare: more entries released at the same instant; walk the ring itself */
-            while (ddeliv != dtail) {
-              const double rel = dring[ddeliv & dmask].release;
-              if (!(rel <= t)) break;
-              if (rel != t) err |= REMY_ERR_ASSERT;
-              ddeliv++;
-            }
-            if (ddeliv != dtail) { const DelayEnt h = dring[ddeliv & dmask]; dhead_release = h.release; dh_sent = h.tick_sent; dh_seq = h.seq; dh_src = h.src; }
-          }
-        }
-        if (ddeliv != dtail) {
-          prefetch_l2(&cold[dh_src]); /* the next ack's sender record: a service time from now */
-          if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
-            const DelayEnt h = dring[(ddeliv + 1) & dmask];
-            dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
-            if (((ddeliv + 1) & 3u) == 3u && (dtail - ddeliv) > 6) prefetch_line(&dring[(ddeliv + 5) & dmask]);
-          }
-        }
-      }
-      /* the tick that reads the mail: same t, no switch can be due, no time passes */
-      mail = (dcons != ddeliv) && (t < duration);
-      if (mail) { iters++; prng_before_shuffle = prng; prng = shuffle_skip(prng, n); }
-    }
+#if REMY_EARLY_COLD
+    /* the acked sender's record is requested before the shuffle's draws, which do not depend on it */
+    SenderCold c_first;
+    if (mail) c_first = cold[m_src];
+#endif
+    /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
+    prng_before_shuffle = prng;
+    prng = shuffle_skip(prng, n);
+    if (!mail) zero_window_lookups(0);
 
     /* ---- 3. receive_feedback for every mailbox (sendergang.cc:175-188) ---- */
     /* the sender acked in this tick usually transmits in this tick: its send state is handed
      * over in registers instead of being re-read from HBM */
-    uint32_t ak_s = 0xFFFFFFFFu, ak_seq = 0; int32_t ak_lim = 0; double ak_isend = 0;
     uint32_t acked = 0; /* senders whose mailbox was read in this tick */
     if (mail) {
-      uint32_t done = 0;
+      uint32_t done = 0, reopened = 0;
       const bool single = (ddeliv - dcons) == 1; /* the usual case: its fields are in m_* */
       for (uint32_t i = dcons; i != ddeliv && !err; i++) {
         const uint32_t s = single ? m_src : dring[i & dmask].src;
         if ((done >> s) & 1u) continue;
         done |= 1u << s;
+#if REMY_EARLY_COLD
+        SenderCold c = c_first;
+        if (i != dcons) c = cold[s];
+#else
         SenderCold c = cold[s];
+#endif
         const int32_t old_ack = c.largest_ack;
         int32_t last_seq = 0;
         for (uint32_t j = i; j != ddeliv; j++) {
@@ -708,6 +721,15 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         } else {
           c.window = whisker_window(c.window, w.window_multiple, w.window_increment);
           c.intersend = w.intersend;
+          /* Rat::send of this same tick (rat-templates.cc:13-18) looks the whisker up again when the window is 0
+           * and applies it to a window of 0: the same leaf (the Memory has not changed), but window(0) = clamp(b)
+           * differs from the 0 = clamp(int(w m + b)) above when m < 0 or w m overflowed - hand-made trees only,
+           * the optimiser keeps 0 <= m <= 1.  (The lookup itself is counted / traced with the other zero-window
+           * lookups of the tick, below.) */
+          if (c.window == 0 && ((on_mask >> s) & 1u)) {
+            const int32_t w0 = whisker_window(0, w.window_multiple, w.window_increment);
+            if (w0 != 0) { c.window = w0; reopened |= 1u << s; }
+          }
         }
         c.leaf = leaf;
         cold[s] = c;
@@ -718,19 +740,35 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
           hot_send[s * HS] = FISH ? fish_due : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
           open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
-          if (COUNT && !FISH) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
+          if (COUNT && !FISH) zero_mask = (c.window == 0 || ((reopened >> s) & 1u)) ? (zero_mask | bit) : (zero_mask & ~bit);
         }
       }
       dcons = ddeliv;
       acked = done;
+      maybe_sends = true;
+      zero_window_lookups(acked);
+      if (COUNT) zero_mask &= ~reopened;
     }
 
-    if (mail) zero_window_lookups(acked);
+    /* (the transmission and link phases, with their chain points, can be gone through more than once per
+     * pass: between two deliveries a busy link sees one departure and about one transmission, in either
+     * order) */
+#pragma unroll 1
+    for (int rep = 0; rep < REMY_SD_REPS; rep++) {
+    /* ---- chain point S: nothing to transmit in this tick and nothing else due at its time, and the next
+     * reference tick starts with a pacing deadline (a departure or delivery at that same time follows in
+     * the phases below) ---- */
+    if (!maybe_sends && chain_ok()) {
+      const double t2 = next_send;
+      if (t2 > t && t2 <= duration && t2 < min_switch && !(pending && pend_release < t2) && !(ddeliv != dtail && dhead_release < t2)) {
+        begin_chained_tick(t2);
+        maybe_sends = true;
+      }
+    }
 
-    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34): the sender phase
-     * of the fused tick if mail was read, else of the tick this pass began with (the scan is skipped when
-     * no deadline is due and nothing changed: next_send stays valid) ---- */
-    if (mail || (!half && maybe_sends)) {
+    /* ---- 4. Rat::send for every sender whose deadline is due (rat-templates.cc:20-34) (the scan is skipped
+     * when no deadline is due and nothing changed: next_send stays valid) ---- */
+    if (maybe_sends) {
       uint32_t ready = 0, ns_sender = 0xFFFFFFFFu;
       uint32_t first_send = 0; /* Fish that looked their lambda up in this tick's send (trace) */
       double ns = DBL_MAX;
@@ -774,9 +812,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                 lring[ltail & lmask] = e; ltail++;
               }
             }
-            if (s == ak_s) ak_seq = seq;
             uint32_t fp = (uint32_t)lim;
             const double x = exp_sample(fp, isend), mx = __ddiv_rn(2.0, isend);
+            if (s == ak_s) { ak_seq = seq; ak_lim = (int32_t)fp; ak_isend = isend; } /* (the phase can come again in this pass) */
             const double st = __dadd_rn(t, __dmul_rn((double)FISH_BATCH, (mx < x) ? mx : x)); /* _update_send_time(tickno) */
             c->packets_sent = seq; c->last_send_time = t; c->intersend = isend; c->window = (int32_t)fp;
             { SendState ss; ss.packets_sent = seq; ss.lim = (int32_t)fp; ss.intersend = isend; sendst[s] = ss; }
@@ -805,11 +843,84 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       next_send = ns;
       /* trace of a Fish tick: per sender, in the shuffled order, the ack's lookup or (never both:
        * an ack sets lambda) the first send's lookup on the all-zero Memory of the reset */
-      if (TRACE && FISH) track_senders(acked, first_send);
-      if (ns_sender != 0xFFFFFFFFu) prefetch_line(&sendst[ns_sender]); /* what its transmission will read */
+      if (TRACE && FISH) { track_senders(acked, first_send); acked = 0; }
+      if (ns_sender != 0xFFFFFFFFu && ns_sender != ak_s) { /* what its transmission will read */
+        const SendState ss = sendst[ns_sender];
+        ak_s = ns_sender; ak_seq = ss.packets_sent; ak_lim = ss.lim; ak_isend = ss.intersend;
+      }
+      maybe_sends = false;
     }
 
-    half = !run_link;
+    /* ---- chain point D: this tick is over (no departure or delivery is due at its time), and the next
+     * reference tick starts with a departure: no switch and no pacing deadline at or before it, no
+     * delivery before it ---- */
+    if (chain_ok() && pending && pend_release > t) {
+      const double t2 = pend_release;
+      if (t2 <= duration && t2 < min_switch && t2 < next_send && !(ddeliv != dtail && dhead_release < t2)) begin_chained_tick(t2);
+    }
+
+    /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
+    if (pending && pend_release <= t) {
+      if (pend_release != t) err |= REMY_ERR_ASSERT;
+      bool lost;
+      if (lossy) lost = canonical(prng) < cfgp->stochastic_loss_rate; /* bernoulli (bits/random.h:3739-3750) */
+      else { prng = lcg_mul(prng, 282475249u); lost = false; } /* two draws, 16807^2 */
+      if (!lost) {
+        if (dtail - dcons >= A.delay_cap) err |= REMY_ERR_DELAY_OVERFLOW;
+        else {
+        DelayEnt e; e.release = __dadd_rn(t, delay); e.tick_sent = pend_sent; e.seq = pend_seq; e.src = pend_src; e.pad[0] = 0; e.pad[1] = 0;
+        dring[dtail & dmask] = e;
+        if (ddeliv == dtail) { /* it is the head of the delay line right away */
+          dhead_release = e.release; dh_sent = e.tick_sent; dh_seq = e.seq; dh_src = e.src;
+        } else if (dtail - ddeliv == 1) { /* ... or the entry right behind the head */
+          dn_release = e.release; dn_sent = e.tick_sent; dn_seq = e.seq; dn_src = e.src;
+        }
+        dtail++;
+        }
+      }
+      pending = false;
+    }
+    if (!pending && lhead != ltail) {
+      const LinkEnt e = lring[lhead & lmask]; lhead++;
+      pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
+    }
+    } /* rep */
+
+    /* ---- chain point V: no delivery is due in this tick, and the next reference tick is a pure delivery:
+     * no switch, pacing deadline or departure at or before the head of the delay line ---- */
+    if (chain_ok() && ddeliv != dtail && dhead_release > t) {
+      const double t2 = dhead_release;
+      if (t2 <= duration && t2 < min_switch && t2 < next_send && !(pending && pend_release <= t2)) begin_chained_tick(t2);
+    }
+
+    /* ---- 7. Delay::tick (delay.hh:53-63) -> Receiver::accept ---- */
+    /* (not written as a loop over the register-held head: a loop's condition would wait for
+     * the ring read issued below, which exists precisely so that nothing waits for it) */
+    if (ddeliv != dtail && dhead_release <= t) {
+      if (dhead_release != t) err |= REMY_ERR_ASSERT;
+      /* Receiver::accept: the delivered packet's fields move to the mail registers */
+      m_sent = dh_sent; m_seq = dh_seq; m_src = dh_src;
+      ddeliv++;
+      if (ddeliv != dtail) {
+        dhead_release = dn_release; dh_sent = dn_sent; dh_seq = dn_seq; dh_src = dn_src;
+        if (dhead_release <= t) { /* rare: more entries released at the same instant; walk the ring itself */
+          while (ddeliv != dtail) {
+            const double rel = dring[ddeliv & dmask].release;
+            if (!(rel <= t)) break;
+            if (rel != t) err |= REMY_ERR_ASSERT;
+            ddeliv++;
+          }
+          if (ddeliv != dtail) { const DelayEnt h = dring[ddeliv & dmask]; dhead_release = h.release; dh_sent = h.tick_sent; dh_seq = h.seq; dh_src = h.src; }
+        }
+      }
+      prefetch_l2(&cold[m_src]); /* the ack's sender record: read at the top of the next pass */
+      if (ddeliv != dtail) {
+        if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
+          const DelayEnt h = dring[(ddeliv + 1) & dmask];
+          dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
+        }
+      }
+    }
   }
 
   /* ---- results: Utility::utility (utility.hh:46-60), SenderGang::utility (sendergang.cc:280-293) ---- */

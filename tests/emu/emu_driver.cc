@@ -153,3 +153,28 @@ static int trace_kind(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const
   }
   return 0;
 }
+
+/* div_small_int (the kernel's division-free dt / k) against the hardware division: n values of dt per
+ * k = 1..32 from a xorshift stream - uniform bit patterns over the positive normal doubles, values
+ * shaped like the simulator's (differences of event times) and neighbours of powers of two.  Returns
+ * the number of mismatches. */
+extern "C" uint64_t remy_emu_check_small_div(uint64_t n, uint64_t seed)
+{
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+  auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  for (uint32_t k = 1; k <= 32; k++) {
+    const double kd = (double)k, inv = 1.0 / kd;
+    for (uint64_t i = 0; i < n; i++) {
+      const uint64_t r = next();
+      double dt;
+      switch (i & 3u) {
+        case 0: { uint64_t b = (r & 0x7fffffffffffffffull); if ((b >> 52) == 0x7ff || (b >> 52) < 64) b = (b & 0xfffffffffffffull) | (0x3ffull << 52); memcpy(&dt, &b, 8); break; }
+        case 1: dt = (double)(r >> 11) * 0x1p-53 * 1000.0; break;                       /* [0, 1000) ms */
+        case 2: dt = (double)((r >> 40) + 1) / (double)(((r >> 8) & 0xffff) + 1); break; /* ratios of small integers */
+        default: { uint64_t b = ((uint64_t)(1023 + (int)(r % 40) - 20) << 52); b += (int64_t)((r >> 8) & 7) - 3; memcpy(&dt, &b, 8); break; } /* 2^e +- a few ulp */
+      }
+      if (remy::div_small_int(dt, kd, inv) != dt / kd) bad++;
+    }
+  }
+  return bad;
+}

@@ -43,8 +43,7 @@ static inline int32_t __double2int_rz(double v)
   return (int32_t)v;
 }
 static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, sizeof r); return r; }
-static inline uint32_t __activemask() { return 1u; }
-static inline uint32_t __reduce_max_sync(uint32_t, uint32_t v) { return v; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 using std::max;
 using std::min;

@@ -30,11 +30,11 @@ def lib(built):
 
 def test_every_declared_symbol_is_exported(lib):
     names = declared_functions()
-    assert len(names) >= 9
+    assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), n
     lib.remy_b200_abi_version.restype = C.c_uint32
-    assert lib.remy_b200_abi_version() == 1
+    assert lib.remy_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -71,6 +71,8 @@ def test_no_gpu_means_loud_failure(lib):
     lib.remy_b200_last_error.restype = C.c_char_p
     assert lib.remy_b200_init(0) == -2
     assert b"no CUDA device" in lib.remy_b200_last_error()
+    assert lib.remy_b200_init_devices(None, 0) == -2   # "all devices" of a machine without any
+    assert lib.remy_b200_device_count() == 0
     with pytest.raises(RuntimeError):
         abi.Device(0)
     tree = abi.default_tree()

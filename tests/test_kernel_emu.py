@@ -160,3 +160,34 @@ def test_emu_config4_sweep(emu, oracle):
         b = oracle.score(tree, cfgs, seeds, want_use_counts=True, threads=16)
         assert (a[0]["error"] == 0).all() and a[0]["packets_sent"].sum() > a[0]["packets_received"].sum() > 100000
         assert_same_results(a, b, what="config4 " + name)
+
+
+def test_emu_negative_window_multiple(emu, oracle):
+    """Trees loaded from files are not confined to the optimiser's 0 <= window_multiple <= 1.  With a
+    negative multiple an ack can close the window (int(w m + b) <= 0) that Rat::send's own lookup at
+    window 0 reopens to b in the same tick (reference src/rat-templates.cc:13-18)."""
+    tree = abi.default_tree()
+    rows = [dict(link_ppt=p, delay=d, num_senders=n, buffer_size=b, mean_on_duration=300, mean_off_duration=100,
+                 simulation_ticks=3000)
+            for p in (0.5, 2) for d in (5, 40) for n in (1, 3, 8) for b in (4, abi.BUFFER_INFINITE)]
+    cfgs = abi.make_configs(rows)
+    seeds = np.arange(len(rows), dtype=np.uint32) + 99
+    cands = np.zeros(5, dtype=abi.leaf_override_dtype)
+    cands[0] = (-1.0, 0.5, 2, 0)      # window 2 -> 0 -> (send) 2 -> ...
+    cands[1] = (-0.5, 0.0, 3, 0)
+    cands[2] = (-2.0, 1.0, 1, 0)
+    cands[3] = (-1.0, 0.25, 0, 0)     # stays closed: b = 0
+    cands[4] = (3000.0, 0.5, 1, 0)    # w m overflows the int conversion after a few acks
+    want = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=4)
+    assert_same_results(emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True), want, what="negative multiple")
+    assert int(want[0]["packets_received"][:len(rows)].min()) > 10
+
+
+def test_small_divisor_division(built):
+    """The kernel divides sending-time increments by the number of active senders with a multiply and
+    two FMAs (sim_kernel.cuh::div_small_int); the result must be the correctly rounded quotient the
+    reference's `/` gives (src/sendergang.cc:169-171)."""
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libremy_emu.so"))
+    lib.remy_emu_check_small_div.restype = C.c_uint64
+    lib.remy_emu_check_small_div.argtypes = [C.c_uint64, C.c_uint64]
+    assert lib.remy_emu_check_small_div(3_200_000, 1) == 0

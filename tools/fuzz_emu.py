@@ -57,7 +57,10 @@ while time.time() < t_end:
         b = orc.score_fish(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=8)
     else:
         cands = helpers.random_candidates(rng, tree, ncand)
-        if rng.integers(0, 3) == 0:   # pacing that is a multiple of the service time; zero windows
+        if rng.integers(0, 6) == 0:   # negative / overflowing window multiples (trees from files are not confined to [0, 1])
+            for c in range(1, ncand):
+                cands[c] = (float(rng.choice([-2.0, -1.0, -0.5, 2500.0])), float(rng.choice([0.0, 0.5, 1.0])), int(rng.choice([0, 1, 2, 5])), int(rng.integers(0, tree.n_leaves)))
+        elif rng.integers(0, 3) == 0:   # pacing that is a multiple of the service time; zero windows
             for c in range(1, ncand):
                 cands[c] = (float(rng.choice([0.0, 0.5, 1.0])), float(rng.choice([0.0, 0.5, 1.0, 2.0])), int(rng.choice([0, 1, 3])), int(rng.integers(0, tree.n_leaves)))
         a = abi._score_with(emu.remy_emu_score_batch, "emu", tree, cfgs, seeds, cands, True, True, [(C.c_uint32, int(rng.choice([0, 0, 16])))])
