@@ -1,23 +1,36 @@
 #!/usr/bin/env python3
-"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout.
+"""bench.py — BASELINE.json's metric on BASELINE.json's configs, one JSON line on stdout.
 
 metric   : simulated packet-events/sec (packet-event = one packet sent by a Rat or one ack
            consumed), whole job over all ranks
-workload : BASELINE configs[1] — the default Remy ConfigRange Evaluator pass (link 1..2 ppt
-           step 0.25 x rtt 100..200 step 25 x nsrc 1..32 = 800 NetConfigs, on = off = 5000 ms,
-           infinite buffer, no loss, fixed WhiskerTree), batched over R evaluator seeds per GPU
-           so that one step fills the machine.  One step = one scoring pass over that batch.
-value    : device time of the kernel launches (one simulation launch + one overflow scan per step) (CUDA events on the launching stream, inside
-           the library), inputs already resident in HBM
+workloads: evaluator-pass (default, the line of record) — BASELINE configs[1]: the default Remy ConfigRange
+           Evaluator pass (link 1..2 ppt step 0.25 x rtt 100..200 step 25 x nsrc 1..32 = 800 NetConfigs,
+           on = off = 5000 ms, infinite buffer, no loss, fixed WhiskerTree), batched over R evaluator seeds
+           per GPU so that one step fills the machine ("scaling": "weak").
+           improve-step — BASELINE configs[2]: every Whisker::next_generation candidate of the most used
+           whisker x the 800 NetConfigs as ONE batch.  With --scaling strong that one batch is partitioned
+           over the ranks by config (remy_b200/sharding.py): each rank scores every candidate on its configs,
+           and only per-simulation utilities (8 bytes each) cross NVLink, summed per candidate in config
+           order on every rank (src/evaluator.cc:96), so the scores are byte-identical for every N.
+           policy-sweep — BASELINE configs[4]: 2^20 random NetConfigs x the candidates, partitioned the same way.
+           One step = one scoring pass over the rank's batch.
+value    : device time of the kernel launches of a step (one simulation launch + one overflow scan; CUDA events
+           on the launching stream, inside the library), inputs already resident in HBM
 e2e      : the same pass through the one-shot C-ABI call with HOST buffers
            (remy_b200_score_batch: H2D copies, scratch allocation, kernels, D2H results)
---impl reference : the reference's own CPU implementation (oracle/_ref, built from
-           /root/reference's sources) on all host threads, on a bounded sample of the workload.
+parity   : the CPU leg scores a sample of the very simulations the GPU just ran; their counters, PRNG end
+           states, event times and utilities are compared in the run ("parity_checked", "parity_ok"), and a
+           mismatch fails the bench.
+--impl reference : the reference's own CPU implementation (oracle/_ref, built from /root/reference's sources)
+           on all host threads, on a bounded sample of the workload (--cpu-shape pool: a fixed pool of
+           hardware_concurrency() workers over the (candidate, config) items; async: the reference's own shape,
+           one std::async thread per candidate scoring its configs serially, src/breeder.cc:57-69).
 
 Launch: python bench.py --gpus N --steps K --warmup W         (N == 1)
         python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -30,17 +43,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from remy_b200 import abi, workloads  # noqa: E402
+from remy_b200 import abi, sharding, workloads  # noqa: E402
 
 METRIC = "sim_packet_events_per_sec"
 UNIT = "packet-events/s"
+INT_FIELDS = ("event_ticks", "packets_sent", "packets_received", "link_queued", "delay_inflight", "prng_state", "error")
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_improve_step(args, dev):
+def build_hash():
+    """Identifies the kernel build a profile capture belongs to: sha256 over the CUDA sources and the ABI header."""
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "remy_b200", "csrc")
+    files = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h")))
+    for f in files + [os.path.join(ROOT, "include", "remy_b200.h")]:
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def improve_step_inputs(args, dev):
     """BASELINE configs[2]: one ActionImprover::evaluate_replacements fan-out (src/breeder.cc:53-77) as ONE
     batch: score the tree once with use counts, take the most used whisker whose action the optimizer may
     vary (WhiskerTree::most_used, src/whiskertree.cc:84-109), generate its candidates with the C++ mirror of
@@ -54,7 +78,7 @@ def build_improve_step(args, dev):
     _, _, counts = dev.score(tree, cfgs, seeds, want_senders=False, want_use_counts=True)
     host = hostlib.HostLib()
     ht = host.tree_from_flat(tree)
-    order = np.argsort(-counts[0].astype(np.int64))
+    order = np.argsort(-counts[0].astype(np.int64), kind="stable")
     for leaf in order:
         l = tree.leaves[leaf]
         if 0 <= l["window_increment"] <= 256 and 0 <= l["window_multiple"] <= 1 and 0.25 <= l["intersend"] <= 3:
@@ -63,7 +87,7 @@ def build_improve_step(args, dev):
     raise SystemExit("no whisker with an optimizable action")
 
 
-def build_workload(args, rank):
+def evaluator_pass_inputs(args, rank):
     tree = workloads.load_golden_tree(args.tree)
     base = workloads.default_config_range(ticks=args.ticks)
     cfgs = np.tile(base, args.replicas)
@@ -72,16 +96,19 @@ def build_workload(args, rank):
     return tree, cfgs, seeds
 
 
-def algorithmic_bytes(cfgs, sims):
-    """per event tick 44 n + 32 n_on bytes of sender state, per packet sent a
-    16-byte queue record written and read once, per delivered packet 32 B in the delay line
-    + 208 B of Memory/Utility/action."""
+def per_packet_bytes(sims):
+    """Compulsory queue and sender-state traffic of the packets themselves: a 16-byte link record
+    written and read once per packet sent; per delivered packet 32 B in the delay line + 208 B of Memory,
+    Utility and action state."""
+    return float((sims["packets_sent"] * 32.0 + sims["packets_received"] * 240.0).sum())
+
+
+def state_in_hbm_bytes(cfgs, cfg_index, sims):
+    """SURVEY.md §8d's model of a design that keeps per-sender state in HBM: additionally 44 n + 32 n_on bytes per
+    event tick.  Reported for reference only: this kernel keeps that state on chip."""
     n = cfgs["num_senders"].astype(np.float64)
     n_on = n * cfgs["mean_on_duration"] / (cfgs["mean_on_duration"] + cfgs["mean_off_duration"])
-    n_cfg = len(cfgs)
-    k = np.arange(len(sims)) % n_cfg
-    return float((sims["event_ticks"] * (44.0 * n[k] + 32.0 * n_on[k]) + sims["packets_sent"] * 32.0
-                  + sims["packets_received"] * 240.0).sum())
+    return float((sims["event_ticks"] * (44.0 * n[cfg_index] + 32.0 * n_on[cfg_index])).sum()) + per_packet_bytes(sims)
 
 
 class ClockSampler:
@@ -134,30 +161,61 @@ def pinned_like(a):
     return out, t
 
 
-def cpu_sample(args, tree, cfgs, seeds):
-    """Bounded sample of the same workload for the CPU leg: every `stride`-th simulation of
-    the first replica."""
-    n_base = len(cfgs) // args.replicas
-    idx = np.arange(0, n_base, args.cpu_stride)
-    return cfgs[idx], seeds[idx], f"every {args.cpu_stride}th NetConfig of one 800-config replica ({len(idx)} simulations, {args.ticks:g} ticks each)"
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
-def run_cpu(args, tree, cfgs, seeds):
-    """Times the reference's own CPU implementation (oracle/_ref) or, if it was not built,
-    the oracle port, on all host threads.  Returns (value, kind, cores, seconds, packet_events)."""
+def run_cpu(tree, cfgs, seeds, cands=None, shape="pool", repeats=1):
+    """Times the reference's own CPU implementation (oracle/_ref) or, if it was not built, the oracle port, on all
+    host threads; best of `repeats`.  Returns a dict (value = packet-events/s) and the per-simulation results."""
+    from oracle import bindings as checkers  # the CPU baseline leg is the one place bench.py executes oracle/
     threads = os.cpu_count() or 1
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libremy_ref.so")
     if os.path.exists(ref_path):
-        lib, kind = abi.Reference(ref_path), "reference"
+        lib, kind = checkers.Reference(ref_path), "reference"
     else:
         import __graft_entry__ as g
         g.build_checkers()
-        lib, kind = abi.Oracle(), "port"
-    t0 = time.perf_counter()
-    sims, _, _ = lib.score(tree, cfgs, seeds, want_senders=False, threads=threads)
-    dt = time.perf_counter() - t0
+        lib, kind, shape = checkers.Oracle(), "port", "pool"
+    best, sims = None, None
+    for _ in range(max(1, repeats)):
+        t0 = time.perf_counter()
+        if shape == "async":
+            sims = lib.score_async_per_candidate(tree, cfgs, seeds, cands=cands)
+        else:
+            sims, _, _ = lib.score(tree, cfgs, seeds, cands=cands, want_senders=False, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
     ev = int((sims["packets_sent"] + sims["packets_received"]).sum())
-    return ev / dt, kind, threads, dt, ev, int(sims["event_ticks"].sum())
+    n_c = 1 if cands is None else len(cands)
+    used = min(threads, n_c) if shape == "async" else threads
+    return {"value": ev / best, "unit": UNIT, "cores": used, "host_threads": threads, "cpu_model": cpu_model(), "kind": kind,
+            "shape": ("one std::async thread per candidate, configs serial (src/breeder.cc:57-69)" if shape == "async"
+                      else "fixed pool of hardware_concurrency() workers over (candidate, config) items; drives the reference's "
+                           "classes through oracle/ref_driver.cc's loop, pinned to the public score() by tests/test_oracle.py"),
+            "seconds": best, "best_of": max(1, repeats), "event_ticks_per_sec": int(sims["event_ticks"].sum()) / best,
+            "sims": int(len(sims))}, sims
+
+
+def check_parity(gpu_sims, cpu_sims):
+    """GPU results of the sampled simulations against the CPU leg's: integers, PRNG end state and event times
+    bit-exact, utilities within 1e-9 relative (the tolerance north_star states)."""
+    bad = []
+    for f in INT_FIELDS:
+        if not (gpu_sims[f] == cpu_sims[f]).all():
+            bad.append(f)
+    if not (gpu_sims["last_tick"] == cpu_sims["last_tick"]).all():
+        bad.append("last_tick")
+    rel = np.abs(gpu_sims["utility"] - cpu_sims["utility"]) <= 1e-9 * np.abs(cpu_sims["utility"])
+    if not rel.all():
+        bad.append("utility")
+    return bad
 
 
 _REAL_STDOUT = None
@@ -186,11 +244,20 @@ def main():
     ap.add_argument("--ticks", type=float, default=1e5, help="simulation_ticks per NetConfig")
     ap.add_argument("--replicas", type=int, default=192, help="evaluator seeds per GPU (x 800 NetConfigs)")
     ap.add_argument("--tree", default="RemyCC-2014-100x")
-    ap.add_argument("--cpu-stride", type=int, default=4)
-    ap.add_argument("--workload", default="evaluator-pass", choices=["evaluator-pass", "improve-step"],
-                    help="evaluator-pass: BASELINE configs[1] (the bench line of record); improve-step: BASELINE configs[2], "
-                         "every Whisker::next_generation candidate of the most used whisker x the 800 NetConfigs in one batch")
+    ap.add_argument("--cpu-stride", type=int, default=4, help="CPU leg: every n-th NetConfig of one replica")
+    ap.add_argument("--cpu-shape", default="pool", choices=["pool", "async"])
+    ap.add_argument("--cpu-repeats", type=int, default=1)
+    ap.add_argument("--workload", default="evaluator-pass", choices=["evaluator-pass", "improve-step", "policy-sweep"])
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="improve-step / policy-sweep: strong = ONE batch partitioned over the ranks (default for them); "
+                         "weak = every rank its own batch (default for evaluator-pass)")
+    ap.add_argument("--sweep-configs", type=int, default=1 << 20, help="policy-sweep: number of random NetConfigs")
+    ap.add_argument("--sweep-candidates", type=int, default=1)
+    ap.add_argument("--parity-sample", type=int, default=200, help="simulations the CPU leg re-scores and compares (0 = off)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity leg")
     args = ap.parse_args()
+    if args.scaling is None:
+        args.scaling = "weak" if args.workload == "evaluator-pass" else "strong"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,31 +265,44 @@ def main():
     if world != args.gpus and world > 1:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}")
     n_gpus = max(world, 1)
-
-    tree, cfgs, seeds = build_workload(args, rank)
-    workload = (f"BASELINE configs[1]: default Remy ConfigRange (800 NetConfigs: link 1-2 ppt x rtt 100-200 ms x nsrc 1-32, "
-                f"exp on/off 5 s, infinite buffer) x {args.replicas} evaluator seeds per GPU, fixed WhiskerTree {args.tree}, "
-                f"{args.ticks:g} ticks")
-    config = {"workload": workload, "sims_per_gpu": int(len(cfgs)), "ticks": args.ticks, "tree": args.tree,
-              "l2": "per-slot simulation state (>200 MB) exceeds the 126 MB L2; a 256 MiB buffer is also written between steps"}
+    l2_note = "per-slot simulation state (>200 MB) exceeds the 126 MB L2; a 256 MiB buffer is also written between steps"
 
     # ------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        scfg, sseed, sample = cpu_sample(args, tree, cfgs, seeds)
+        if args.workload != "evaluator-pass":
+            tree = workloads.load_golden_tree(args.tree)
+            base = workloads.default_config_range(ticks=args.ticks)
+            cands = workloads.candidate_grid(0, base=(2, 0.9, 1.0), n=(os.cpu_count() or 1))
+            idx = np.arange(0, len(base), 8)
+            scfg, sseed = base[idx], workloads.seeds_for(2026, len(base))[idx]
+            sample = (f"{len(cands)} candidates (one per host thread) x every 8th NetConfig of the default ConfigRange "
+                      f"({len(idx)} configs), {args.ticks:g} ticks")
+            workload = f"BASELINE configs[2] shape: candidates x NetConfigs of one improve step, {args.ticks:g} ticks (CPU sample)"
+        else:
+            tree, cfgs, seeds = evaluator_pass_inputs(args, 0)
+            n_base = len(cfgs) // args.replicas
+            idx = np.arange(0, n_base, args.cpu_stride)
+            scfg, sseed, cands = cfgs[idx], seeds[idx], None
+            sample = f"every {args.cpu_stride}th NetConfig of one 800-config replica ({len(idx)} simulations, {args.ticks:g} ticks each)"
+            workload = (f"BASELINE configs[1]: default Remy ConfigRange (800 NetConfigs: link 1-2 ppt x rtt 100-200 ms x nsrc 1-32, "
+                        f"exp on/off 5 s, infinite buffer) x {args.replicas} evaluator seeds per GPU, fixed WhiskerTree {args.tree}, "
+                        f"{args.ticks:g} ticks")
+        config = {"workload": workload, "ticks": args.ticks, "tree": args.tree, "l2": l2_note}
         for _ in range(min(args.warmup, 1)):
-            run_cpu(args, tree, scfg[:32], sseed[:32])
-        tot_t, tot_ev, tot_ticks = 0.0, 0, 0
+            run_cpu(tree, scfg[:32], sseed[:32], cands, args.cpu_shape)
+        tot_t, tot_ev, tot_ticks, cpu = 0.0, 0, 0, None
         for _ in range(args.steps):
-            v, kind, cores, dt, ev, ticks = run_cpu(args, tree, scfg, sseed)
-            tot_t += dt; tot_ev += ev; tot_ticks += ticks
+            cpu, sims = run_cpu(tree, scfg, sseed, cands, args.cpu_shape)
+            tot_t += cpu["seconds"]; tot_ev += int((sims["packets_sent"] + sims["packets_received"]).sum())
+            tot_ticks += int(sims["event_ticks"].sum())
         value = tot_ev / tot_t
+        cpu.update({"value": value, "sample": sample})
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "event_ticks_per_sec": tot_ticks / tot_t,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "event_ticks_per_sec": tot_ticks / tot_t, "cpu_baseline": cpu,
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -248,25 +328,52 @@ def main():
         flush_buf.fill_(1)
         torch.cuda.synchronize()
 
-    cands = None
-    if args.workload == "improve-step":
-        tree, cfgs, seeds, cands, leaf = build_improve_step(args, dev)
-        config["workload"] = (f"BASELINE configs[2]: one RatBreeder improve fan-out — {len(cands)} Whisker::next_generation candidates of "
-                              f"leaf {leaf} of {args.tree} x 800 NetConfigs (default ConfigRange), {args.ticks:g} ticks, one batch per GPU")
-        config["sims_per_gpu"] = int(len(cands) * len(cfgs))
-        args.replicas = 1
+    # ---- the rank's batch: (tree, candidates, this rank's configs) ----
+    cands, shard, layout, n_cfgs_all = None, None, None, None
+    if args.workload == "evaluator-pass":
+        tree, cfgs, seeds = evaluator_pass_inputs(args, rank)
+        workload = (f"BASELINE configs[1]: default Remy ConfigRange (800 NetConfigs: link 1-2 ppt x rtt 100-200 ms x nsrc 1-32, "
+                    f"exp on/off 5 s, infinite buffer) x {args.replicas} evaluator seeds per GPU, fixed WhiskerTree {args.tree}, "
+                    f"{args.ticks:g} ticks")
+        n_units = 800.0
+    else:
+        if args.workload == "improve-step":
+            tree, cfgs, seeds, cands, leaf = improve_step_inputs(args, dev)
+            workload = (f"BASELINE configs[2]: one RatBreeder improve fan-out - {len(cands)} Whisker::next_generation candidates of "
+                        f"leaf {leaf} of {args.tree} x 800 NetConfigs (default ConfigRange), {args.ticks:g} ticks")
+        else:
+            tree = workloads.load_golden_tree(args.tree)
+            cfgs = workloads.random_sweep(args.sweep_configs, ticks=args.ticks)
+            seeds = workloads.seeds_for(2026, len(cfgs))
+            cands = workloads.candidate_grid(0, base=(2, 0.9, 1.0), n=args.sweep_candidates) if args.sweep_candidates > 1 else None
+            workload = (f"BASELINE configs[4]: {len(cfgs)} random NetConfigs (link U[0.5,10] ppt, delay U[25,200] ms, nsrc U{{1..32}}, buffer in "
+                        f"{{10, 0.1 BDP, BDP, infinite}}, loss in {{0, .01, .05}}, on = off = 5 s) x {args.sweep_candidates} candidate(s), "
+                        f"{args.ticks:g} ticks, {args.tree}")
+        n_cfgs_all = len(cfgs)
+        n_units = float(n_cfgs_all)
+        if args.scaling == "strong" and world > 1:
+            # ONE batch over all ranks: deal the cost-sorted configs round-robin (every rank keeps every candidate)
+            layout = sharding.shard_layout(cfgs, world)
+            shard = layout[rank]
+            cfgs, seeds = cfgs[shard], seeds[shard]
+            workload += f"; ONE batch partitioned over {world} GPUs by config"
+        elif world > 1:
+            workload += "; every GPU scores its own copy of the batch"
+    n_cands = 1 if cands is None else len(cands)
+    config = {"workload": workload, "sims_per_gpu": int(n_cands * len(cfgs)), "ticks": args.ticks, "tree": args.tree, "l2": l2_note}
 
-    # value: staged API, inputs resident in HBM
+    # ---- value: staged API, inputs resident in HBM ----
     batch = dev.create_batch(tree, cfgs, seeds, cands=cands, want_senders=False, want_use_counts=False)
     for _ in range(args.warmup):
         batch.run(timed=True)
         flush_l2()
     sampler = ClockSampler(local_rank)
     barrier()
-    kernel_ms, launches = 0.0, 0
+    kernel_ms, launches, rerun = 0.0, 0, 0
     for _ in range(args.steps):
         kernel_ms += batch.run(timed=True)  # CUDA events on the library's launching stream
         launches += batch.launches()
+        rerun = batch.rerun()
         flush_l2()
     barrier()
     clocks = sampler.stop()
@@ -275,13 +382,14 @@ def main():
     assert (sims["error"] == 0).all(), np.unique(sims["error"])
     pk = int((sims["packets_sent"] + sims["packets_received"]).sum())
     ticks = int(sims["event_ticks"].sum())
-    alg_bytes = algorithmic_bytes(cfgs[:len(cfgs) // args.replicas], sims)
+    cfg_index = np.arange(len(sims)) % len(cfgs)
+    pp_bytes = per_packet_bytes(sims)
+    model_bytes = state_in_hbm_bytes(cfgs, cfg_index, sims)
 
-    # e2e: one-shot C-ABI call, host (pinned) buffers in and out
+    # ---- e2e: one-shot C-ABI call, host (pinned) buffers in and out ----
     p_cfgs, k1 = pinned_like(cfgs)
     p_seeds, k2 = pinned_like(seeds)
-    for _ in range(1):
-        dev.score(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
+    dev.score(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -293,17 +401,62 @@ def main():
     h2d = int(p_cfgs.nbytes + p_seeds.nbytes + tree.nodes.nbytes * 96 // 112 + tree.leaves.nbytes + len(cfgs) * 4)
     d2h = int(e_sims.nbytes)
 
-    # reduce over ranks: max time, summed work; the per-rank score crosses NVLink (tiny)
+    # ---- per-candidate scores: only per-simulation utilities cross NVLink (strong scaling), summed in config order ----
+    scores_sha, reduce_ms = None, None
+    if cands is not None or args.workload == "policy-sweep":
+        util = torch.from_numpy(np.ascontiguousarray(sims["utility"].reshape(n_cands, len(cfgs)))).cuda()
+        if shard is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            full = sharding.gather_utilities(util, n_cfgs_all, rank, world, dist, layout)
+            ev1.record(); torch.cuda.synchronize()
+            reduce_ms = ev0.elapsed_time(ev1)
+        else:
+            full = util
+        cand_scores = sharding.scores_in_config_order(full.cpu().numpy())
+        scores_sha = hashlib.sha256(cand_scores.tobytes()).hexdigest()[:16]
+
+    # ---- reduce over ranks: max time, summed work ----
     t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
-    w = torch.tensor([float(pk), float(ticks), float(len(sims)), alg_bytes, float(launches), score], dtype=torch.float64, device="cuda")
+    w = torch.tensor([float(pk), float(ticks), float(len(sims)), pp_bytes, float(launches), score, model_bytes, float(rerun)],
+                     dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
     kernel_ms_max, e2e_s_max = t.tolist()
-    pk_all, ticks_all, sims_all, alg_all, launches_all, score_all = w.tolist()
+    pk_all, ticks_all, sims_all, pp_all, launches_all, score_all, model_all, rerun_all = w.tolist()
+
+    # ---- CPU leg on rank 0 (N = 1 only): baseline timing + in-run parity on the same simulations ----
+    cpu, parity_n, parity_bad = None, 0, []
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        rng = np.random.default_rng(7)
+        if args.workload == "evaluator-pass":
+            n_base = len(cfgs) // args.replicas
+            kidx = np.arange(0, n_base, args.cpu_stride)
+            sample = f"every {args.cpu_stride}th NetConfig of one 800-config replica ({len(kidx)} simulations, {args.ticks:g} ticks each)"
+            scand = None
+        else:
+            kidx = np.sort(rng.choice(len(cfgs), size=min(len(cfgs), max(1, args.parity_sample)), replace=False))
+            scand = cands
+            sample = f"{len(kidx)} random NetConfigs of the batch x {n_cands} candidate(s) ({args.ticks:g} ticks each)"
+            if cands is not None and len(cands) > 8:   # bound the CPU work: a few candidates on a few configs
+                csel = np.sort(rng.choice(len(cands), size=8, replace=False))
+                kidx = kidx[:max(1, args.parity_sample // 8)]
+                scand = cands[csel]
+                sample = f"8 random candidates x {len(kidx)} random NetConfigs of the batch ({args.ticks:g} ticks each)"
+        cpu, c_sims = run_cpu(tree, cfgs[kidx], seeds[kidx], scand, args.cpu_shape, args.cpu_repeats)
+        cpu["sample"] = sample
+        if args.parity_sample > 0:
+            g = sims.reshape(n_cands, len(cfgs))
+            if scand is not None and scand is not cands:
+                g = g[csel]
+            g = g[:, kidx].reshape(-1)
+            parity_n = len(g)
+            parity_bad = check_parity(g, c_sims)
 
     if rank == 0:
         secs = kernel_ms_max / 1e3
+        step_s = secs / args.steps
         value = pk_all * args.steps / secs
         peaks = {}
         try:
@@ -311,42 +464,59 @@ def main():
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_all / n_gpus / (kernel_ms_max / args.steps / 1e3) / 1e9  # per GPU, per launch
-        traffic = None
+        # measured DRAM traffic of this build's launch on this workload, if a capture of the same build exists
+        bh = build_hash()
+        wkey = f"{args.workload}/{args.ticks:g}/{args.replicas if args.workload == 'evaluator-pass' else n_cands}/{args.tree}/{config['sims_per_gpu']}"
+        log(f"traffic key: {wkey}   build hash: {bh}")
+        traffic, counters, tnote = None, None, "no ncu capture of this build and workload under profiles/traffic.json"
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
-        except (OSError, ValueError):
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("build_hash") == bh and tj.get("workload_key") == wkey:
+                traffic = float(tj["dram_bytes_per_launch"])
+                tnote = tj.get("source", "profiles/traffic.json")
+            elif tj.get("build_hash") != bh:
+                tnote = f"profiles/traffic.json was captured on build {tj.get('build_hash')}, this is {bh}: refused"
+            else:
+                tnote = f"profiles/traffic.json is for workload {tj.get('workload_key')}, this is {wkey}: refused"
+            if tj.get("build_hash") == bh:
+                counters = tj.get("counters")
+        except (OSError, ValueError, KeyError):
             pass
-        scfg, sseed, sample = cpu_sample(args, tree, cfgs, seeds)
-        cpu = None
-        if n_gpus == 1:
-            v, kind, cores, dt, ev, _ = run_cpu(args, tree, scfg, sseed)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "seconds": dt}
+        pp_gbs = pp_all / n_gpus / step_s / 1e9
+        if traffic is not None:
+            achieved, basis = traffic / step_s / 1e9, "measured DRAM bytes of the step's simulation launch (ncu, same build) / launch time"
+        else:
+            achieved, basis = pp_gbs, "per-packet algorithmic bytes (32 B per packet sent + 240 B per ack, SURVEY.md 8d) / launch time"
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "basis": basis, "traffic_note": tnote, "build_hash": bh,
+                    "per_packet_algorithmic_gbs": pp_gbs, "per_packet_frac": pp_gbs / peak,
+                    "state_in_hbm_model_gbs": model_all / n_gpus / step_s / 1e9,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "kernel_counters": counters,
+                    "note": "The kernel is bound by memory latency and issue slots, not by HBM bandwidth (kernel_counters: ncu --set full of the "
+                            "same build, profiles/). state_in_hbm_model_gbs is SURVEY.md 8d's figure for a design that keeps per-sender state in "
+                            "HBM (44n+32n_on B per event tick on top of the per-packet bytes); this kernel keeps that state on chip, so the "
+                            "figure can exceed the peak and is not a roofline fraction."}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": pk_all * args.steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches_all),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic,
-                             "dram_gbs": (traffic / (kernel_ms_max / args.steps / 1e3) / 1e9) if traffic else None,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                             "note": "achieved = SURVEY.md 8d algorithmic bytes (a design that keeps per-sender state in HBM: 44n+32n_on B "
-                                     "per event tick + 32 B per packet sent + 240 B per ack) / step time. This kernel caches event minima and "
-                                     "masks in registers/shared memory, so its real DRAM traffic (`traffic`, ncu dram bytes of the step's one "
-                                     "simulation launch, profiles/traffic.json) is ~9x smaller and `frac` can exceed 1; `dram_gbs` is the HBM "
-                                     "bandwidth actually used. The path is latency/issue bound (ncu --set full, profiles/r01_ncu_full_final.txt: "
-                                     "30% issue slots, 14.4/32 lanes, long-scoreboard 6.0 cycles per issued instruction; captured with 4 resident "
-                                     "blocks per SM, the library now builds with 3), not HBM bound."},
-                "cpu_baseline": cpu,
+                "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu,
+                "parity_checked": parity_n, "parity_ok": (not parity_bad) if parity_n else None,
                 "event_ticks_per_sec": ticks_all * args.steps / secs, "sims_per_sec": sims_all * args.steps / secs,
-                "evals_per_sec": sims_all / 800.0 * args.steps / secs, "score_sum": score_all}
+                "evals_per_sec": sims_all / n_units * args.steps / secs, "sims_rerun_with_larger_rings": int(rerun_all),
+                "score_sum": score_all}
         if cands is not None:
             line["candidates"] = int(len(cands))
+        if scores_sha is not None:
+            line["candidate_scores_sha256"] = scores_sha
+            line["score_gather_ms"] = reduce_ms
         emit(line)
+        if parity_bad:
+            log(f"bench.py: PARITY FAILURE on the in-run sample: fields {parity_bad} differ between the GPU and the CPU reference")
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 1 if parity_bad else 0
 
 
 if __name__ == "__main__":

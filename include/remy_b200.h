@@ -92,7 +92,8 @@ typedef struct RemyLeafOverride {
 #define REMY_ERR_NO_CHILD       0x02u /* interior node, no child matched [assert(false), whiskertree.cc:80] */
 #define REMY_ERR_LINK_OVERFLOW  0x04u /* link queue exceeded this library's ring capacity [no equivalent] */
 #define REMY_ERR_DELAY_OVERFLOW 0x08u /* delay line exceeded ring capacity [no equivalent] */
-#define REMY_ERR_BAD_CONFIG     0x10u /* num_senders 0 or > REMY_MAX_SENDERS, ticks <= 0, rate <= 0 */
+#define REMY_ERR_BAD_CONFIG     0x10u /* num_senders 0 or > REMY_MAX_SENDERS, ticks <= 0, rate <= 0, a negative or NaN mean
+                                       * on/off duration or both 0 [the reference's switch loop never ends, sendergang.cc:95-105] */
 #define REMY_ERR_ASSERT         0x20u /* a live reference assert would have fired (memory.cc:68-69, delay.hh:47,59) */
 
 typedef struct RemySimResult {

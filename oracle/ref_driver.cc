@@ -240,6 +240,40 @@ extern "C" int remy_ref_score_batch(const RemyFlatTree *tree,
   return 0;
 }
 
+/* The reference's own fan-out SHAPE (src/breeder.cc:57-69): one std::async(std::launch::async, ...) task per
+ * candidate - an OS thread each, no pool - that copies the tree, applies its replacement and scores ALL configs
+ * serially; the futures are drained in submission order (src/breeder.cc:73-77, 130-134).  Per-simulation seeds as
+ * everywhere in this repository.  Wall time = the slowest candidate on however many cores exist. */
+extern "C" int remy_ref_score_batch_async(const RemyFlatTree *tree,
+                                          const RemyLeafOverride *cands, uint32_t n_cands,
+                                          const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                          RemySimResult *out_sims, int mode)
+{
+  if (!tree || !cfgs || !seeds || !out_sims) return REMY_EINVAL;
+  if (!cands) n_cands = 1;
+  std::vector<std::future<double>> scores;
+  for (uint32_t c = 0; c < n_cands; c++) {
+    scores.emplace_back(std::async(std::launch::async, [=]() {
+      const RemyLeafOverride *ov = (cands && cands[c].leaf_index != REMY_NO_OVERRIDE) ? &cands[c] : nullptr;
+      RemyBuffers::WhiskerTree dna;
+      build_dna(tree, 0, ov, &dna);
+      WhiskerTree t(dna);
+      t.reset_counts();
+      std::vector<RemySenderResult> tmp(4096);
+      double score = 0;
+      for (uint32_t k = 0; k < n_cfgs; k++) {
+        RemySimResult *out = &out_sims[(size_t)c * n_cfgs + k];
+        if (mode == 0) run_whitebox(t, cfgs[k], seeds[k], out, tmp.data());
+        else run_public(t, cfgs[k], seeds[k], out, tmp.data());
+        score += out->utility; /* src/evaluator.cc:96 */
+      }
+      return score;
+    }));
+  }
+  for (auto &f : scores) f.get();
+  return 0;
+}
+
 /* libstdc++/glibc arithmetic the reference relies on, exposed so the tests can
  * pin the oracle's restatements against the real library code. */
 extern "C" double remy_ref_exponential(uint32_t *state, double rate)

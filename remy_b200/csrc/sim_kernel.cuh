@@ -70,9 +70,6 @@ constexpr uint32_t INC_BUF = 16;  /* buffered sending-time increments per simula
 #ifndef REMY_CHAIN
 #define REMY_CHAIN 1 /* chained ticks (see run_sim); 0 = one reference tick per pass of the event loop */
 #endif
-#ifndef REMY_EARLY_COLD
-#define REMY_EARLY_COLD 0
-#endif
 #ifndef REMY_SD_REPS
 #define REMY_SD_REPS 2 /* times the transmission + link phases are gone through per pass */
 #endif
@@ -349,7 +346,10 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   res.link_queued = 0; res.delay_inflight = 0; res.prng_state = 0; res.error = 0;
 
   const uint32_t n = cfg.num_senders;
-  if (n == 0 || n > A.n_max || n > REMY_MAX_SENDERS || !(cfg.simulation_ticks > 0) || !(cfg.link_ppt > 0)) {
+  /* (on/off durations: a negative or NaN mean, or both means 0, would keep the switch loop below - and the
+   * reference's, src/sendergang.cc:95-105 - from ever ending; on a GPU that hangs the device, so it is refused) */
+  const bool bad_durations = !(cfg.mean_on_duration >= 0) || !(cfg.mean_off_duration >= 0) || !(cfg.mean_on_duration + cfg.mean_off_duration > 0);
+  if (n == 0 || n > A.n_max || n > REMY_MAX_SENDERS || !(cfg.simulation_ticks > 0) || !(cfg.link_ppt > 0) || bad_durations) {
     res.error = REMY_ERR_BAD_CONFIG;
     A.out_sims[sim] = res;
     if (A.out_senders) {
@@ -645,11 +645,6 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       ninc++;
     }
 
-#if REMY_EARLY_COLD
-    /* the acked sender's record is requested before the shuffle's draws, which do not depend on it */
-    SenderCold c_first;
-    if (mail) c_first = cold[m_src];
-#endif
     /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
     prng_before_shuffle = prng;
     prng = shuffle_skip(prng, n);
@@ -666,12 +661,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         const uint32_t s = single ? m_src : dring[i & dmask].src;
         if ((done >> s) & 1u) continue;
         done |= 1u << s;
-#if REMY_EARLY_COLD
-        SenderCold c = c_first;
-        if (i != dcons) c = cold[s];
-#else
         SenderCold c = cold[s];
-#endif
         const int32_t old_ack = c.largest_ack;
         int32_t last_seq = 0;
         for (uint32_t j = i; j != ddeliv; j++) {

@@ -414,4 +414,12 @@ int remy_host_apply_best_split(void *h, const void *range_bytes, size_t range_si
     return 0;)
 }
 
+/* Evaluator<WhiskerTree>::seeds: the per-config seeds of one Evaluator (INTEGRATION.md shows the same rule). */
+int remy_host_seeds(unsigned int prng_seed, uint32_t *out, uint32_t n)
+{
+  GUARD(const std::vector<uint32_t> s = Evaluator<WhiskerTree>::seeds(prng_seed, n);
+        for (uint32_t i = 0; i < n; i++) out[i] = s[i];
+        return 0;)
+}
+
 } /* extern "C" */

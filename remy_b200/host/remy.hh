@@ -18,6 +18,7 @@
 #define REMY_HOST_REMY_HH
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <utility>
 #include <vector>
@@ -243,6 +244,26 @@ public:
    * successive outputs of minstd_rand0(prng_seed) */
   static std::vector<uint32_t> seeds(unsigned int prng_seed, size_t n);
 };
+
+/* dev= option of the CLIs: "N" binds one CUDA device, "N,M,..." or "all" several - every batch (an
+ * evaluator pass, the candidates of an improve step) is then partitioned over them by the library
+ * (remy_b200_init_devices), the way the reference spreads an improve step over the cores of one machine
+ * (src/breeder.cc:53-77).  Returns the library's return code. */
+inline int init_devices(const std::string &spec)
+{
+  if (spec == "all") return remy_b200_init_devices(nullptr, 0);
+  std::vector<int> devs;
+  size_t pos = 0;
+  while (pos <= spec.size()) {
+    const size_t comma = spec.find(',', pos);
+    const std::string tok = spec.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+    if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
+    if (comma == std::string::npos) break;
+    pos = comma + 1;
+  }
+  if (devs.empty()) devs.push_back(0);
+  return remy_b200_init_devices(devs.data(), (int)devs.size());
+}
 
 } // namespace remy_b200
 #endif

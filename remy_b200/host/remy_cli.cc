@@ -6,7 +6,7 @@
  * SURVEY.md Appendix A).  Every run optimises the whisker actions and then bisects the most used
  * whisker (RatBreeder::improve incl. apply_best_split, see breeder.hh).
  * Extensions: runs=N (stop after N improve() rounds; default: forever, like the reference),
- *             seed=N (default time ^ pid), dev=N.
+ *             seed=N (default time ^ pid), dev=N | N,M,... | all (several GPUs share every batch).
  */
 #include <cstdio>
 #include <cstdlib>
@@ -50,7 +50,7 @@ int main(int argc, char *argv[])
   WhiskerImproverOptions whisker_options;
   unsigned int seed = 0;
   long max_runs = -1;
-  int device = 0;
+  string device = "0";
 
   for (int i = 1; i < argc; i++) {
     const string arg(argv[i]);
@@ -81,14 +81,23 @@ int main(int argc, char *argv[])
       }
     } else if (key == "runs=") max_runs = atol(val.c_str());
     else if (key == "seed=") seed = (unsigned int)strtoul(val.c_str(), nullptr, 10);
-    else if (key == "dev=") device = atoi(val.c_str());
+    else if (key == "dev=") device = val;
   }
   if (config_filename.empty()) {
     fprintf(stderr, "An input configuration protobuf must be provided via the cf= option. \n");
     fprintf(stderr, "You can generate one using './configuration'. \n");
     return 1;
   }
-  if (remy_b200_init(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
+  /* The shipped config/*.cfg files are ConfigRangeUnicorn files whose field 76 is a flow length in packets for
+   * ByteSwitchedSender, -2 meaning unbounded (src/sendergang.cc:128-134).  The Rat path switches senders in time
+   * (TimeSwitchedSender): a non-positive "on" would never let the switch loop end, so it is mapped to the
+   * sender-runner default of 5000 ms (src/sender-runner.cc:53), like sender_runner.cc does for cf=. */
+  if (options.config_range.mean_on_duration.low <= 0) {
+    fprintf(stderr, "mean_on_duration %f..%f is not a duration (a ByteSwitchedSender flow length?): using 5000 ms\n",
+            options.config_range.mean_on_duration.low, options.config_range.mean_on_duration.high);
+    options.config_range.mean_on_duration = Range(5000, 5000, 0);
+  }
+  if (remy_b200::init_devices(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
 
   RatBreeder breeder(options, whisker_options, seed);
   printf("#######################\n");

@@ -3,7 +3,7 @@
  * key=value arguments (if= of= cf=), same stdout, same checkpoint files (`<of>.<run>` = the FinTree with
  * its config (93), optimizer (94) and configvector (95) sub-messages).  Every run optimises the fins'
  * lambdas and then bisects the most used fin (FishBreeder::improve, fish.hh).
- * Extensions: runs=N (default: forever, like the reference), seed=N (default time ^ pid), dev=N.
+ * Extensions: runs=N (default: forever, like the reference), seed=N (default time ^ pid), dev=N | N,M,... | all (several GPUs share every batch).
  */
 #include <cstdio>
 #include <cstdlib>
@@ -34,7 +34,7 @@ int main(int argc, char *argv[])
   BreederOptions options;
   unsigned int seed = 0;
   long max_runs = -1;
-  int device = 0;
+  string device = "0";
 
   for (int i = 1; i < argc; i++) {
     const string arg(argv[i]);
@@ -56,14 +56,14 @@ int main(int argc, char *argv[])
     } else if (key == "of=") output_filename = val;
     else if (key == "runs=") max_runs = atol(val.c_str());
     else if (key == "seed=") seed = (unsigned int)strtoul(val.c_str(), nullptr, 10);
-    else if (key == "dev=") device = atoi(val.c_str());
+    else if (key == "dev=") device = val;
   }
   if (config_filename.empty()) {
     fprintf(stderr, "An input configuration protobuf must be provided via the cf= option. \n");
     fprintf(stderr, "You can generate one using './configuration'. \n");
     return 1;
   }
-  if (remy_b200_init(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
+  if (remy_b200::init_devices(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
 
   FishBreeder breeder(options, seed);
   const ConfigRange &cr = options.config_range;

@@ -7,7 +7,7 @@
  *   if= nsrc= link= rtt= on= off= buf= sloss=
  * Extensions (the reference has none of these): seed=N (default: time ^ pid, src/random.cc:9),
  *   ticks=N (default 1000000, src/sender-runner.cc:57), cf=FILE (a config/ .cfg ConfigRange[Unicorn]
- *   file, mapped as in SURVEY.md Appendix A: every *.low; on <= 0 -> 5000 ms), dev=N.
+ *   file, mapped as in SURVEY.md Appendix A: every *.low; on <= 0 -> 5000 ms), dev=N | N,M,... | all (several GPUs share every batch).
  */
 #include <cmath>
 #include <cstdio>
@@ -90,7 +90,7 @@ int main(int argc, char *argv[])
   double buffer_size = numeric_limits<unsigned int>::max();
   double stochastic_loss_rate = 0;
   unsigned int simulation_ticks = 1000000, seed = 0;
-  int device = 0;
+  string device = "0";
 
   for (int i = 1; i < argc; i++) {
     string arg(argv[i]);
@@ -143,7 +143,7 @@ int main(int argc, char *argv[])
     } else if (key == "ticks=") {
       simulation_ticks = (unsigned int)strtoul(val.c_str(), nullptr, 10);
     } else if (key == "dev=") {
-      device = atoi(val.c_str());
+      device = val;
     }
   }
   num_senders = (unsigned int)nsrc_arg;
@@ -158,7 +158,7 @@ int main(int argc, char *argv[])
   configuration_range.stochastic_loss_rate = Range(stochastic_loss_rate, stochastic_loss_rate, 0);
   configuration_range.simulation_ticks = simulation_ticks;
 
-  if (remy_b200_init(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
+  if (remy_b200::init_devices(device)) { fprintf(stderr, "remy_b200_init: %s\n", remy_b200_last_error()); return 1; }
   /* parse_outcome (src/sender-runner.cc:27-43) */
   auto parse_outcome = [](double score, const vector<pair<NetConfig, vector<pair<double, double>>>> &tds, const string &rules) {
     printf("score = %f\n", score);

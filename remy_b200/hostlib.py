@@ -72,6 +72,13 @@ class HostLib:
     def err(self):
         return self.lib.remy_host_last_error().decode()
 
+    def seeds(self, prng_seed, n):
+        """Evaluator<WhiskerTree>::seeds(prng_seed, n) of the C++ host mirror."""
+        out = np.zeros(n, dtype=np.uint32)
+        self.lib.remy_host_seeds.argtypes = [C.c_uint, C.c_void_p, C.c_uint32]
+        self._check(self.lib.remy_host_seeds(prng_seed, out.ctypes.data, n) == 0)
+        return out
+
     def p2_median(self, samples):
         a = np.ascontiguousarray(samples, dtype=np.float64)
         return self.lib.remy_host_p2_median(a.ctypes.data, len(a))

@@ -22,18 +22,18 @@ def built():
 
 @pytest.fixture(scope="session")
 def oracle(built):
-    from remy_b200 import abi
-    return abi.Oracle()
+    from oracle import bindings as checkers
+    return checkers.Oracle()
 
 
 @pytest.fixture(scope="session")
 def reference(built):
     """The reference's own sources (oracle/_ref); only where it was built."""
-    from remy_b200 import abi
+    from oracle import bindings as checkers
     path = os.path.join(ROOT, "oracle", "_ref", "libremy_ref.so")
     if not os.path.exists(path):
         pytest.skip("oracle/_ref/libremy_ref.so not built (needs /root/reference)")
-    return abi.Reference(path)
+    return checkers.Reference(path)
 
 
 @pytest.fixture(scope="session")

@@ -143,9 +143,11 @@ def test_gpu_error_words(device):
                             dict(link_ppt=1, num_senders=2, simulation_ticks=0),
                             dict(link_ppt=0, num_senders=2, simulation_ticks=10),
                             dict(link_ppt=1, num_senders=33, simulation_ticks=10),
+                            dict(link_ppt=1, num_senders=2, simulation_ticks=10, mean_on_duration=0, mean_off_duration=0),
+                            dict(link_ppt=1, num_senders=2, simulation_ticks=10, mean_on_duration=-2, mean_off_duration=500),
                             dict(link_ppt=1, num_senders=2, simulation_ticks=100)])
-    sims, _, _ = device.score(abi.default_tree(), bad, np.arange(5, dtype=np.uint32))
-    assert sims["error"].tolist() == [abi.ERR_BAD_CONFIG] * 4 + [0]
+    sims, _, _ = device.score(abi.default_tree(), bad, np.arange(len(bad), dtype=np.uint32))
+    assert sims["error"].tolist() == [abi.ERR_BAD_CONFIG] * 6 + [0]
 
 
 def test_gpu_argument_errors(device):

@@ -9,6 +9,7 @@ import pytest
 from remy_b200 import abi, dna, hostlib, workloads
 
 REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -172,3 +173,21 @@ def test_wire_formats_against_python_protobuf(host):
             r.throughput, r.delay = 0.5 + s + k, 151.25 * (s + 1)
     answer = a.SerializeToString()
     assert host.answer_roundtrip(answer) == answer
+
+
+def test_per_config_seed_rule(host):
+    """One rule in three places: the C++ host mirror (Evaluator::seeds), the Python workloads (seeds_for) and the
+    binding shown in INTEGRATION.md - config 0 runs on the Evaluator's seed itself (what the reference's loop
+    starts with, src/evaluator.cc:84, so that a single-config score stays bit-identical to the reference's),
+    config k >= 1 on the k-th output of minstd_rand0(seed)."""
+    for seed in (0, 1, 12345, 2147483647, 2147483648, 4294967295):
+        got = host.seeds(seed, 9)
+        assert (got == workloads.seeds_for(seed, 9)).all(), seed
+        x = seed % 2147483647 or 1      # what `PRNG seeder(prng_seed)` holds (bits/random.tcc:116-126)
+        want = [seed]
+        for _ in range(8):
+            x = x * 16807 % 2147483647
+            want.append(x)               # seeder() in the INTEGRATION.md snippet
+        assert got.tolist() == want, seed
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert "seeds.empty() ? prng_seed : (uint32_t)seeder()" in text

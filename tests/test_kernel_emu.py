@@ -91,8 +91,12 @@ def test_emu_error_words(emu, oracle):
     bad = abi.make_configs([dict(link_ppt=1, num_senders=0, simulation_ticks=100),
                             dict(link_ppt=1, num_senders=2, simulation_ticks=0),
                             dict(link_ppt=0, num_senders=2, simulation_ticks=10),
-                            dict(link_ppt=1, num_senders=33, simulation_ticks=10)])
-    a = emu.score(abi.default_tree(), bad, np.arange(4, dtype=np.uint32))
+                            dict(link_ppt=1, num_senders=33, simulation_ticks=10),
+                            # durations with which the on/off switch loop (src/sendergang.cc:95-105) never ends
+                            dict(link_ppt=1, num_senders=2, simulation_ticks=10, mean_on_duration=0, mean_off_duration=0),
+                            dict(link_ppt=1, num_senders=2, simulation_ticks=10, mean_on_duration=-2, mean_off_duration=500),
+                            dict(link_ppt=1, num_senders=2, simulation_ticks=10, mean_on_duration=50, mean_off_duration=float("nan"))])
+    a = emu.score(abi.default_tree(), bad, np.arange(len(bad), dtype=np.uint32))
     assert (a[0]["error"] == abi.ERR_BAD_CONFIG).all()
 
 

@@ -15,11 +15,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import helpers  # noqa: E402
 from remy_b200 import abi, workloads  # noqa: E402
+from oracle import bindings as checkers  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "libremy_emu.so"))
-orc = abi.Oracle()
+orc = checkers.Oracle()
 for name in ("remy_emu_trace", "remy_emu_trace_fish"):
     getattr(emu, name).argtypes = [C.POINTER(abi.FlatTreeC), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]

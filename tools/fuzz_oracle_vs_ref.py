@@ -12,10 +12,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import helpers  # noqa: E402
 from remy_b200 import abi, workloads  # noqa: E402
+from oracle import bindings as checkers  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 300.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-orc, ref = abi.Oracle(), abi.Reference()
+orc, ref = checkers.Oracle(), checkers.Reference()
 t_end = time.time() + budget
 it = 0
 while time.time() < t_end:

@@ -9,9 +9,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import helpers  # noqa: E402
 from remy_b200 import abi, workloads  # noqa: E402
+from oracle import bindings as checkers  # noqa: E402
 
 libs = sys.argv[1:] or [None]
-orc = abi.Oracle()
+orc = checkers.Oracle()
 for lib in libs:
     dev = abi.Device(0, path=lib)
     bad = 0

@@ -19,6 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from remy_b200 import abi, dna  # noqa: E402
+from oracle import bindings as checkers  # noqa: E402
 
 REF_TESTS = "/root/reference/tests"
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -79,7 +80,7 @@ def main():
         t = dna.load_dna(os.path.join(REF_TESTS, name + ".dna"))
         np.savez_compressed(os.path.join(OUT, "trees", name + ".npz"), nodes=t.nodes, leaves=t.leaves)
         trees[name] = t
-    ref = abi.Reference()
+    ref = checkers.Reference()
     out = []
     for case in CASES:
         tree_names = [case["tree"]] if case["tree"] else TREES[1:]
