@@ -213,7 +213,7 @@ int alloc_scratch(DevBatch *b, Scratch &s, uint32_t slots, uint32_t n_max, uint3
 /* Shared memory and residency of the kernel for a launch that accepts up to n_max senders. */
 int launch_geometry(DevBatch *b, uint32_t n_max, size_t &smem, bool &tree_in_smem, uint32_t &resident_blocks)
 {
-  tree_in_smem = smem_bytes(b, n_max, true) <= 160 * 1024 && b->tree_bytes <= 64 * 1024;
+  tree_in_smem = smem_bytes(b, n_max, true) <= (SIM_BLOCK > 128 ? SIM_SMEM_MAX : (size_t)160 * 1024) && b->tree_bytes <= 64 * 1024;
   smem = smem_bytes(b, n_max, tree_in_smem);
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_fn(b), SIM_BLOCK, smem));
@@ -253,12 +253,12 @@ int bind_device(int device, int count)
   c->device = device; c->sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   /* the kernel stages the tree in shared memory: allow the large carve-out (a per-device attribute) */
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
   g_ctx.push_back(std::move(c));
   return 0;
 }

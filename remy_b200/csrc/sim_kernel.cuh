@@ -959,7 +959,12 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   }
 }
 
-constexpr int SIM_BLOCK = 128;
+#ifndef REMY_SIM_BLOCK
+#define REMY_SIM_BLOCK 128
+#endif
+constexpr int SIM_BLOCK = REMY_SIM_BLOCK;
+/* dynamic shared memory a block may ask for (the sm_100 opt-in maximum is 227 KB per block) */
+constexpr size_t SIM_SMEM_MAX = 226 * 1024;
 #ifndef REMY_MIN_BLOCKS_PER_SM
 /* Three resident blocks per SM = 168 registers per thread and no spills.  Four (128 registers, 44 B of
  * spills and re-reads of per-simulation constants) gave 33 % more warps but measured 10 % slower on the
