@@ -219,6 +219,30 @@ int remy_b200_batch_create_fish(const RemyFlatTree *tree,
                                 uint32_t sender_stride, int want_senders, int want_use_counts,
                                 RemyBatch **out_batch);
 
+/* ---- flow-length workloads: Rat senders behind ByteSwitchedSender ---------------------- *
+ * Replaces: Network<SenderGang<Rat, ByteSwitchedSender<Rat>>, ...>::run_simulation - the reference's
+ * flow-length sender switch (src/sendergang.cc:108-138, 256-278; src/rat-templates.cc:22-26), which the
+ * reference itself instantiates only for its RL sender (src/unicornevaluator.cc:109,140) but which is what
+ * `on = -2` / `on = 80` mean in the shipped config/*.cfg files.  A sender is switched on after an
+ * exponential idle time (mean_off_duration, ms) and switches itself off when it has SENT its flow;
+ * RemyNetConfig.mean_on_duration is the mean flow length in PACKETS (length = lrint(ceil(Exp(1/mean))));
+ * mean_on_duration <= 0 = unbounded flows (INT_MAX packets); mean_off_duration must be > 0 (REMY_ERR_BAD_CONFIG
+ * otherwise: with an idle time of 0 the reference starts flow after flow in one instant and never leaves that tick).
+ * Everything else as remy_b200_score_batch.
+ * There is no trace == true variant. */
+int remy_b200_score_batch_flows(const RemyFlatTree *tree,
+                                const RemyLeafOverride *cands, uint32_t n_cands,
+                                const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                uint32_t sender_stride,
+                                RemySimResult *out_sims,
+                                RemySenderResult *out_senders,
+                                uint32_t *out_use_counts);
+int remy_b200_batch_create_flows(const RemyFlatTree *tree,
+                                 const RemyLeafOverride *cands, uint32_t n_cands,
+                                 const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                 uint32_t sender_stride, int want_senders, int want_use_counts,
+                                 RemyBatch **out_batch);
+
 /* ---- trace == true scoring ------------------------------------------------ *
  * Replaces: Evaluator<WhiskerTree>::score(tree, trace = true) (src/evaluator.cc:77-103 with
  * Rat::_track set, src/rat.cc:8-20), the call Breeder::apply_best_split makes

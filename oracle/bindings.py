@@ -28,6 +28,11 @@ class Oracle(_ScoreLib):
         return _score_with(self.lib.remy_oracle_score_batch_kind, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
                            [(C.c_uint32, threads), (C.c_int, 1)])
 
+    def score_flows(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1):
+        """Rat senders behind ByteSwitchedSender (src/sendergang.cc:108-138, 256-278) restated: flows of a random length in packets."""
+        return _score_with(self.lib.remy_oracle_score_batch_kind, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
+                           [(C.c_uint32, threads), (C.c_int, 2)])
+
     def trace_sim(self, tree, cfg, seed, cap=1 << 22, fish=False):
         """Every use_whisker / use_fin call of one simulation, in call order: (sim result, leaf[n], mem[n, 6])."""
         f = self.lib.remy_oracle_trace_sim_kind
@@ -97,6 +102,11 @@ class Reference(_ScoreLib):
         """The reference's own Fish / FinTree code (src/evaluator.cc:105-132)."""
         return _score_with(self.lib.remy_ref_score_batch_fish, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
                            [(C.c_uint32, threads), (C.c_int, mode)])
+
+    def score_flows(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False, threads=1):
+        """The reference's own ByteSwitchedSender template instantiated for Rat."""
+        return _score_with(self.lib.remy_ref_score_batch_flows, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
+                           [(C.c_uint32, threads)])
 
     def trace_split(self, tree, cfgs, seeds, generation=0, split=True):
         """The reference's own trace == true scoring (per config, on one tree) and, if `split`, the

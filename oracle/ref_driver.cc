@@ -73,6 +73,10 @@ namespace {
 
 typedef SenderGang<Rat, TimeSwitchedSender<Rat>> RatGang;
 typedef Network<RatGang, RatGang> RatNetwork;
+/* The reference instantiates ByteSwitchedSender for its RL sender only (src/unicornevaluator.cc:109,140); the class
+ * template itself is generic (src/sendergang.cc:108-138, 256-278), so the checker instantiates it for Rat. */
+typedef SenderGang<Rat, ByteSwitchedSender<Rat>> RatFlowGang;
+typedef Network<RatFlowGang, RatFlowGang> RatFlowNetwork;
 
 RemyBuffers::Memory memory_dna(const double *v)
 {
@@ -128,12 +132,13 @@ NetConfig to_netconfig(const RemyNetConfig &c)
   return x;
 }
 
-void run_whitebox(WhiskerTree &tree, const RemyNetConfig &c, uint32_t seed,
-                  RemySimResult *out, RemySenderResult *snd)
+template <class Net>
+void run_whitebox_t(WhiskerTree &tree, const RemyNetConfig &c, uint32_t seed,
+                    RemySimResult *out, RemySenderResult *snd)
 {
   PRNG run_prng(seed);
   const NetConfig x = to_netconfig(c);
-  RatNetwork net(Rat(tree, false), run_prng, x);
+  Net net(Rat(tree, false), run_prng, x);
   const double duration = c.simulation_ticks;
   uint64_t iters = 0;
   while (net._tickno < duration) { /* src/network.cc:73-84 */
@@ -169,6 +174,11 @@ void run_whitebox(WhiskerTree &tree, const RemyNetConfig &c, uint32_t seed,
   out->delay_inflight = infl;
   std::ostringstream os; os << run_prng;
   out->prng_state = (uint32_t)std::stoul(os.str());
+}
+
+void run_whitebox(WhiskerTree &tree, const RemyNetConfig &c, uint32_t seed, RemySimResult *out, RemySenderResult *snd)
+{
+  run_whitebox_t<RatNetwork>(tree, c, seed, out, snd);
 }
 
 void run_public(WhiskerTree &tree, const RemyNetConfig &c, uint32_t seed,
@@ -217,6 +227,56 @@ extern "C" int remy_ref_score_batch(const RemyFlatTree *tree,
       t.reset_counts();          /* src/evaluator.cc:86 */
       if (mode == 0) run_whitebox(t, cfgs[k], seeds[k], &out_sims[s], tmp.data());
       else run_public(t, cfgs[k], seeds[k], &out_sims[s], tmp.data());
+      if (out_senders) {
+        RemySenderResult *dst = &out_senders[(size_t)s * sender_stride];
+        memset(dst, 0, sizeof(RemySenderResult) * sender_stride);
+        memcpy(dst, tmp.data(), sizeof(RemySenderResult) * std::min(sender_stride, cfgs[k].num_senders));
+      }
+      if (out_use_counts) {
+        std::vector<unsigned> counts;
+        collect_counts(t, counts);
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t l = 0; l < counts.size() && l < tree->n_leaves; l++)
+          out_use_counts[(size_t)c * tree->n_leaves + l] += counts[l];
+      }
+    }
+  };
+  if (n_threads <= 1) worker();
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t i = 0; i < n_threads; i++) th.emplace_back(worker);
+    for (auto &t : th) t.join();
+  }
+  return 0;
+}
+
+/* Rat senders behind the reference's ByteSwitchedSender: cfgs[k].mean_on_duration is the mean flow length in packets
+ * (<= 0: unbounded flows).  White-box loop only: no public entry point of the reference builds this network. */
+extern "C" int remy_ref_score_batch_flows(const RemyFlatTree *tree,
+                                          const RemyLeafOverride *cands, uint32_t n_cands,
+                                          const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                          uint32_t sender_stride,
+                                          RemySimResult *out_sims, RemySenderResult *out_senders,
+                                          uint32_t *out_use_counts, uint32_t n_threads)
+{
+  if (!tree || !cfgs || !seeds || !out_sims) return REMY_EINVAL;
+  if (!cands) n_cands = 1;
+  const uint32_t total = n_cands * n_cfgs;
+  if (out_use_counts) memset(out_use_counts, 0, sizeof(uint32_t) * (size_t)n_cands * tree->n_leaves);
+  std::atomic<uint32_t> next(0);
+  std::mutex mu;
+  auto worker = [&]() {
+    std::vector<RemySenderResult> tmp(4096);
+    for (;;) {
+      const uint32_t s = next.fetch_add(1);
+      if (s >= total) break;
+      const uint32_t c = s / n_cfgs, k = s % n_cfgs;
+      const RemyLeafOverride *ov = (cands && cands[c].leaf_index != REMY_NO_OVERRIDE) ? &cands[c] : nullptr;
+      RemyBuffers::WhiskerTree dna;
+      build_dna(tree, 0, ov, &dna);
+      WhiskerTree t(dna);
+      t.reset_counts();
+      run_whitebox_t<RatFlowNetwork>(t, cfgs[k], seeds[k], &out_sims[s], tmp.data());
       if (out_senders) {
         RemySenderResult *dst = &out_senders[(size_t)s * sender_stride];
         memset(dst, 0, sizeof(RemySenderResult) * sender_stride);

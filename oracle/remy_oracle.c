@@ -262,6 +262,7 @@ typedef struct {
   utility_t utility;
   int sending;
   unsigned id;
+  unsigned packets_sent_cap; /* ByteSwitchedSender::packets_sent_cap_ (src/sendergang.hh:77) */
 } sender_t;
 
 typedef struct { pkt_t *a; size_t len, cap; } mailbox_t; /* Receiver::_collector[src] (src/receiver.hh:13) */
@@ -282,7 +283,8 @@ typedef struct {
   mailbox_t *collector; uint32_t collector_size;
   double tickno;
   uint32_t err;
-  int kind;                /* 0 = Rat over a WhiskerTree, 1 = Fish over a FinTree (leaf lambda in RemyLeafAction.intersend) */
+  int kind;                /* 0 = Rat over a WhiskerTree, 1 = Fish over a FinTree (leaf lambda in RemyLeafAction.intersend),
+                            * 2 = Rat behind ByteSwitchedSender: flows of a random length in packets (mean_on_duration = mean length) */
 } net_t;
 
 /* Rat::reset (src/rat.cc:34-48); Memory::reset (src/memory.hh:93). */
@@ -332,7 +334,12 @@ static void link_accept(net_t *N, const pkt_t *p, double tickno)
 }
 
 /* Rat::send (src/rat-templates.cc:8-35). */
+static void rat_send_capped(net_t *N, rat_t *r, unsigned id, double tickno, unsigned packets_sent_cap);
 static void rat_send(net_t *N, rat_t *r, unsigned id, double tickno)
+{
+  rat_send_capped(N, r, id, tickno, 0xFFFFFFFFu); /* default argument: numeric_limits<unsigned int>::max() (src/rat.hh) */
+}
+static void rat_send_capped(net_t *N, rat_t *r, unsigned id, double tickno, unsigned packets_sent_cap)
 {
   if (r->the_window == 0) {
     RemyLeafAction w;
@@ -342,6 +349,7 @@ static void rat_send(net_t *N, rat_t *r, unsigned id, double tickno)
   }
   if (((int)r->packets_sent < r->largest_ack + 1 + r->the_window)
       && (r->last_send_time + r->intersend_time <= tickno)) {
+    if (r->packets_sent >= packets_sent_cap) return; /* "Have we reached the end of the flow for now?" (rat-templates.cc:23-26) */
     pkt_t p; p.src = id; p.tick_sent = tickno; p.tick_received = -1; p.seq_num = r->packets_sent;
     r->packets_sent++;
     link_accept(N, &p, tickno);
@@ -423,8 +431,25 @@ static void switcher(net_t *N, sender_t *s, double tickno, unsigned num_sending)
   while (s->next_switch_tick <= tickno) {
     if (s->next_switch_tick != tickno) N->err |= REMY_ERR_ASSERT; /* sendergang.cc:98 */
     if (s->sending) { accumulate(s, tickno, num_sending); s->sending = 0; }
-    else { s->sending = 1; if (N->kind) fish_reset(&s->rat, &s->fish); else rat_reset(N, &s->rat); s->internal_tick = tickno; }
+    else { s->sending = 1; if (N->kind == 1) fish_reset(&s->rat, &s->fish); else rat_reset(N, &s->rat); s->internal_tick = tickno; }
     s->next_switch_tick += exp_sample(&N->prng, s->sending ? N->stop_rate : N->start_rate);
+    if (N->err & (REMY_ERR_NO_WHISKER | REMY_ERR_NO_CHILD)) return;
+  }
+}
+
+/* ByteSwitchedSender::switcher (src/sendergang.cc:108-138): switched on by the clock, off by the flow's length. */
+static void byte_switcher(net_t *N, sender_t *s, double tickno)
+{
+  while (s->next_switch_tick <= tickno) {
+    if (s->next_switch_tick != tickno) N->err |= REMY_ERR_ASSERT;
+    if (s->sending) { N->err |= REMY_ERR_ASSERT; return; }       /* "never sets a time to switch off" */
+    s->sending = 1; rat_reset(N, &s->rat); s->internal_tick = tickno; /* switch_on (sendergang.cc:140-149) */
+    s->next_switch_tick = DBL_MAX;
+    unsigned new_flow_length;
+    if (N->stop_rate > 0) new_flow_length = (unsigned)lrint(ceil(exp_sample(&N->prng, N->stop_rate)));
+    else new_flow_length = (unsigned)INT_MAX;                       /* "Using (almost) infinite flows..." */
+    if (!(new_flow_length > 0)) N->err |= REMY_ERR_ASSERT;
+    s->packets_sent_cap += new_flow_length;
     if (N->err & (REMY_ERR_NO_WHISKER | REMY_ERR_NO_CHILD)) return;
   }
 }
@@ -440,12 +465,20 @@ static void sender_tick(net_t *N, sender_t *s, double tickno, unsigned num_sendi
       if (!(mb->a[i].tick_received >= mb->a[i].tick_sent)) N->err |= REMY_ERR_ASSERT;
       s->utility.total_delay += mb->a[i].tick_received - mb->a[i].tick_sent;
     }
-    if (N->kind) fish_packets_received(N, &s->rat, &s->fish, mb->a, mb->len);
+    if (N->kind == 1) fish_packets_received(N, &s->rat, &s->fish, mb->a, mb->len);
     else rat_packets_received(N, &s->rat, mb->a, mb->len);
     mb->len = 0;
   }
-  if (s->sending) {
-    if (N->kind) fish_send(N, &s->rat, &s->fish, s->id, tickno);
+  if (s->sending && N->kind == 2) { /* ByteSwitchedSender::tick (src/sendergang.cc:256-278) */
+    if (!(s->rat.packets_sent < s->packets_sent_cap)) N->err |= REMY_ERR_ASSERT;
+    rat_send_capped(N, &s->rat, s->id, tickno, s->packets_sent_cap);
+    accumulate(s, tickno, num_sending);
+    if (s->rat.packets_sent == s->packets_sent_cap) { /* do we need to switch ourselves off? */
+      accumulate(s, tickno, num_sending); s->sending = 0; /* switch_off */
+      s->next_switch_tick = tickno + exp_sample(&N->prng, N->start_rate);
+    }
+  } else if (s->sending) {
+    if (N->kind == 1) fish_send(N, &s->rat, &s->fish, s->id, tickno);
     else rat_send(N, &s->rat, s->id, tickno);
     accumulate(s, tickno, num_sending);
   }
@@ -474,7 +507,7 @@ static void net_tick(net_t *N)
   /* SenderGangofGangs::tick (src/sendergangofgangs.cc:44-53); gang 2 is empty. */
   unsigned num_sending = count_active(N);
   for (uint32_t i = 0; i < N->n; i++) {
-    switcher(N, &N->gang[i], t, num_sending);
+    if (N->kind == 2) byte_switcher(N, &N->gang[i], t); else switcher(N, &N->gang[i], t, num_sending);
     if (N->err & (REMY_ERR_NO_WHISKER | REMY_ERR_NO_CHILD)) return;
   }
   num_sending = count_active(N);
@@ -573,7 +606,7 @@ void remy_oracle_run_sim_kind(const RemyFlatTree *tree, const RemyLeafOverride *
   net_t N; memset(&N, 0, sizeof N);
   prng_seed(&N.prng, seed);
   N.kind = kind;
-  const uint32_t fish_prng_seed = kind ? prng_next(&N.prng) : 0;
+  const uint32_t fish_prng_seed = kind == 1 ? prng_next(&N.prng) : 0;
   N.pol.tree = tree;
   N.pol.ov = (ov && ov->leaf_index != REMY_NO_OVERRIDE) ? ov : NULL;
   N.pol.use_counts = use_counts;
@@ -588,7 +621,7 @@ void remy_oracle_run_sim_kind(const RemyFlatTree *tree, const RemyLeafOverride *
     s->id = i;
     s->next_switch_tick = exp_sample(&N.prng, N.start_rate);
     s->rat.largest_ack = -1;
-    if (kind) prng_seed(&s->fish.prng, fish_prng_seed);
+    if (kind == 1) prng_seed(&s->fish.prng, fish_prng_seed);
   }
   N.delay = cfg->delay;
   N.service = 1.0 / cfg->link_ppt;
@@ -602,7 +635,7 @@ void remy_oracle_run_sim_kind(const RemyFlatTree *tree, const RemyLeafOverride *
     double s_next = DBL_MAX;
     for (uint32_t i = 0; i < N.n; i++) {
       const sender_t *s = &N.gang[i];
-      const double ev = dmin(s->next_switch_tick, s->sending ? (kind ? fish_next_event_time(&s->fish, N.tickno) : rat_next_event_time(&s->rat, N.tickno)) : DBL_MAX);
+      const double ev = dmin(s->next_switch_tick, s->sending ? (kind == 1 ? fish_next_event_time(&s->fish, N.tickno) : rat_next_event_time(&s->rat, N.tickno)) : DBL_MAX);
       if (ev < s_next) s_next = ev;
     }
     const double link_next = N.pending.len ? N.pending.a[N.pending.head].release : DBL_MAX;

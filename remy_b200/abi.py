@@ -234,8 +234,9 @@ class Device(_ScoreLib):
             getattr(self.lib, name).restype = C.c_uint32
             getattr(self.lib, name).argtypes = [_PTR]
         if self.abi_version >= 2:
-            self.lib.remy_b200_batch_create_fish.restype = C.c_int
-            self.lib.remy_b200_batch_create_fish.argtypes = self.lib.remy_b200_batch_create.argtypes
+            for name in ("remy_b200_batch_create_fish", "remy_b200_batch_create_flows"):
+                getattr(self.lib, name).restype = C.c_int
+                getattr(self.lib, name).argtypes = self.lib.remy_b200_batch_create.argtypes
 
     def last_error(self):
         return self.lib.remy_b200_last_error().decode()
@@ -244,6 +245,13 @@ class Device(_ScoreLib):
         """remy_b200_score_batch_fish: Fish senders over a FinTree on the GPU."""
         try:
             return _score_with(self.lib.remy_b200_score_batch_fish, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts, [])
+        except RuntimeError as e:
+            raise RuntimeError(f"{e}: {self.last_error()}")
+
+    def score_flows(self, tree, cfgs, seeds, cands=None, want_senders=True, want_use_counts=False):
+        """remy_b200_score_batch_flows: Rat senders behind ByteSwitchedSender (mean_on_duration = mean flow length in packets)."""
+        try:
+            return _score_with(self.lib.remy_b200_score_batch_flows, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts, [])
         except RuntimeError as e:
             raise RuntimeError(f"{e}: {self.last_error()}")
 
@@ -279,14 +287,14 @@ class Device(_ScoreLib):
             out.append((a[:, 0].astype(np.uint32), np.ascontiguousarray(a[:, 1:]).view(np.float64)))
         return sims, senders, counts, out
 
-    def create_batch(self, tree, cfgs, seeds, cands=None, want_senders=False, want_use_counts=False, fish=False):
-        return DeviceBatch(self, tree, cfgs, seeds, cands, want_senders, want_use_counts, fish)
+    def create_batch(self, tree, cfgs, seeds, cands=None, want_senders=False, want_use_counts=False, fish=False, flows=False):
+        return DeviceBatch(self, tree, cfgs, seeds, cands, want_senders, want_use_counts, fish, flows)
 
 
 class DeviceBatch:
     """Staged scoring: inputs stay resident in HBM between runs."""
 
-    def __init__(self, dev, tree, cfgs, seeds, cands, want_senders, want_use_counts, fish=False):
+    def __init__(self, dev, tree, cfgs, seeds, cands, want_senders, want_use_counts, fish=False, flows=False):
         self.dev = dev
         self.tree = tree
         self.cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
@@ -298,7 +306,8 @@ class DeviceBatch:
         self.want_senders = want_senders
         self.want_use_counts = want_use_counts
         h = _PTR()
-        create = dev.lib.remy_b200_batch_create_fish if fish else dev.lib.remy_b200_batch_create
+        create = (dev.lib.remy_b200_batch_create_fish if fish else dev.lib.remy_b200_batch_create_flows if flows
+                  else dev.lib.remy_b200_batch_create)
         rc = create(tree.byref(), _ptr(self.cands), self.n_cands, _ptr(self.cfgs),
                                             _ptr(self.seeds), len(self.cfgs), self.stride,
                                             int(want_senders), int(want_use_counts), C.byref(h))

@@ -123,7 +123,8 @@ struct DevBatch {
   uint32_t launches = 0, redone = 0;
   /* trace == true scoring (remy_b200_score_trace): 0 = off, 1 = counting run, 2 = writing run */
   int trace = 0; uint32_t trace_words = 0;
-  bool fish = false; /* Fish senders over a FinTree (remy_b200_score_batch_fish) */
+  bool fish = false;  /* Fish senders over a FinTree (remy_b200_score_batch_fish) */
+  bool flows = false; /* Rat senders behind ByteSwitchedSender (remy_b200_score_batch_flows) */
   DevBuf<uint64_t> trace_log, trace_off, out_lookups;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   ~DevBatch()
@@ -152,6 +153,7 @@ const void *kernel_fn(const DevBatch *b)
 {
   if (b->trace) return b->fish ? (const void *)remy_sim_kernel<true, true, true> : (const void *)remy_sim_kernel<true, true>;
   if (b->fish) return b->want_counts ? (const void *)remy_sim_kernel<true, false, true> : (const void *)remy_sim_kernel<false, false, true>;
+  if (b->flows) return b->want_counts ? (const void *)remy_sim_kernel<true, false, false, true> : (const void *)remy_sim_kernel<false, false, false, true>;
   return b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
 }
 
@@ -234,6 +236,8 @@ int launch(DevBatch *b, const Scratch &s, size_t smem, bool tree_in_smem, const 
   else if (b->trace) remy_sim_kernel<true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->fish && b->want_counts) remy_sim_kernel<true, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->fish) remy_sim_kernel<false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else if (b->flows && b->want_counts) remy_sim_kernel<true, false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  else if (b->flows) remy_sim_kernel<false, false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
   else remy_sim_kernel<false><<<grid, SIM_BLOCK, smem, stream>>>(a);
   CU(cudaGetLastError());
@@ -259,6 +263,8 @@ int bind_device(int device, int count)
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
   CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
   g_ctx.push_back(std::move(c));
   return 0;
 }
@@ -268,7 +274,7 @@ int bind_device(int device, int count)
 int create_part(DeviceCtx *ctx, const RemyFlatTree *tree, const PreparedTree &pt,
                 const RemyLeafOverride *cands, uint32_t n_cands,
                 const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
-                uint32_t sender_stride, bool want_senders, bool want_counts, int trace, bool fish,
+                uint32_t sender_stride, bool want_senders, bool want_counts, int trace, int kind,
                 const BatchPlan &plan, const std::vector<uint32_t> *pairs, std::unique_ptr<DevBatch> &out)
 {
   CU(cudaSetDevice(ctx->device));
@@ -281,7 +287,8 @@ int create_part(DeviceCtx *ctx, const RemyFlatTree *tree, const PreparedTree &pt
   b->want_senders = want_senders; b->want_counts = want_counts;
   b->sender_stride = sender_stride;
   b->trace = trace;
-  b->fish = fish;
+  b->fish = kind == 1;
+  b->flows = kind == 2;
   b->n_nodes = tree->n_nodes; b->n_leaves = tree->n_leaves; b->axes_mask = pt.axes_mask; b->tree_bytes = pt.bytes();
   b->trace_words = 1u + (uint32_t)__builtin_popcount(pt.axes_mask);
   b->delay_cap = plan.delay_cap;
@@ -457,10 +464,11 @@ static int create_impl(const RemyFlatTree *tree,
                        const RemyLeafOverride *cands, uint32_t n_cands,
                        const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
                        uint32_t sender_stride, int want_senders, int want_use_counts, int trace,
-                       RemyBatch **out_batch, bool fish = false)
+                       RemyBatch **out_batch, int kind = 0 /* 0 Rat, 1 Fish, 2 Rat behind ByteSwitchedSender */)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!out_batch) return fail(REMY_EINVAL, "out_batch is NULL");
+  if (kind == 2 && trace) return fail(REMY_EINVAL, "no lookup log for flow-switched senders");
   *out_batch = nullptr;
   if (g_ctx.empty()) return fail(REMY_ENODEV, "remy_b200_init has not been called");
   if (!tree || !tree->nodes || !tree->leaves || tree->n_nodes == 0 || tree->n_leaves == 0)
@@ -498,7 +506,7 @@ static int create_impl(const RemyFlatTree *tree,
     std::vector<uint32_t> pairs;
     if (n_dev > 1) for (size_t i = d; i < plan.order.size(); i += n_dev) pairs.push_back(plan.order[i]);
     int rc = create_part(g_ctx[d].get(), tree, pt, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride,
-                         B->want_senders, B->want_counts, trace, fish, plan, n_dev > 1 ? &pairs : nullptr, part);
+                         B->want_senders, B->want_counts, trace, kind, plan, n_dev > 1 ? &pairs : nullptr, part);
     if (rc) return rc;
     B->parts.push_back(std::move(part));
   }
@@ -522,7 +530,16 @@ int remy_b200_batch_create_fish(const RemyFlatTree *tree,
                                 uint32_t sender_stride, int want_senders, int want_use_counts,
                                 RemyBatch **out_batch)
 {
-  return create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, want_senders, want_use_counts, 0, out_batch, true);
+  return create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, want_senders, want_use_counts, 0, out_batch, 1);
+}
+
+int remy_b200_batch_create_flows(const RemyFlatTree *tree,
+                                 const RemyLeafOverride *cands, uint32_t n_cands,
+                                 const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                 uint32_t sender_stride, int want_senders, int want_use_counts,
+                                 RemyBatch **out_batch)
+{
+  return create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, want_senders, want_use_counts, 0, out_batch, 2);
 }
 
 int remy_b200_batch_run(RemyBatch *B, float *kernel_ms)
@@ -652,7 +669,24 @@ int remy_b200_score_batch_fish(const RemyFlatTree *tree,
 {
   if (!out_sims && n_cfgs) return fail(REMY_EINVAL, "out_sims is NULL");
   RemyBatch *b = nullptr;
-  int rc = create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, out_use_counts != nullptr, 0, &b, true);
+  int rc = create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, out_use_counts != nullptr, 0, &b, 1);
+  if (rc) return rc;
+  rc = remy_b200_batch_run(b, nullptr);
+  if (!rc) rc = remy_b200_batch_fetch(b, out_sims, out_senders, out_use_counts);
+  remy_b200_batch_destroy(b);
+  return rc;
+}
+
+/* ---- Rat senders behind ByteSwitchedSender: flows of a random length in packets ------------- */
+int remy_b200_score_batch_flows(const RemyFlatTree *tree,
+                                const RemyLeafOverride *cands, uint32_t n_cands,
+                                const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                uint32_t sender_stride,
+                                RemySimResult *out_sims, RemySenderResult *out_senders, uint32_t *out_use_counts)
+{
+  if (!out_sims && n_cfgs) return fail(REMY_EINVAL, "out_sims is NULL");
+  RemyBatch *b = nullptr;
+  int rc = create_impl(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, out_use_counts != nullptr, 0, &b, 2);
   if (rc) return rc;
   rc = remy_b200_batch_run(b, nullptr);
   if (!rc) rc = remy_b200_batch_fetch(b, out_sims, out_senders, out_use_counts);
@@ -696,7 +730,7 @@ static int score_trace_impl(const RemyFlatTree *tree,
   /* (trace batches live on the first bound device: one tree, one log) */
   /* 1. counting run: scores, use counts, and the number of lookups of every simulation */
   RemyBatch *B = nullptr;
-  int rc = create_impl(tree, nullptr, 1, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, 1, 1, &B, fish);
+  int rc = create_impl(tree, nullptr, 1, cfgs, seeds, n_cfgs, sender_stride, out_senders != nullptr, 1, 1, &B, fish ? 1 : 0);
   if (rc) return rc;
   std::vector<uint64_t> lookups(n_cfgs);
   const uint32_t words = B->parts[0]->trace_words;
@@ -737,7 +771,7 @@ static int score_trace_impl(const RemyFlatTree *tree,
     while (g1 < n_cfgs && (g1 == g0 || (recs + lookups[g1]) * rec_bytes <= budget)) { offs.push_back(recs); recs += lookups[g1]; g1++; }
     if (recs * rec_bytes > budget && recs * rec_bytes > ((uint64_t)64 << 30)) { rc = fail(REMY_ENOMEM, "trace of one simulation exceeds the log budget"); break; }
     RemyBatch *G = nullptr;
-    rc = create_impl(tree, nullptr, 1, cfgs + g0, seeds + g0, g1 - g0, sender_stride, 0, 1, 2, &G, fish);
+    rc = create_impl(tree, nullptr, 1, cfgs + g0, seeds + g0, g1 - g0, sender_stride, 0, 1, 2, &G, fish ? 1 : 0);
     if (rc) break;
     DevBatch *g = G->parts[0].get();
     {

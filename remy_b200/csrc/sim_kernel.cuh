@@ -329,8 +329,14 @@ __device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int
  * Fish::_prng, the pacing deadline (Fish::_next_send_time, 0 = at once) lives in hot_send[];
  * SendState mirrors {packets_sent, prng, lambda}. */
 constexpr uint32_t FISH_BATCH = 5; /* Fish::_batch_size (src/fish.cc:20) */
+/* BYTESW selects ByteSwitchedSender<Rat> (src/sendergang.cc:108-138, 256-278) instead of TimeSwitchedSender<Rat>: a sender
+ * is switched ON after an exponential idle time and switches itself OFF when it has sent its flow, whose length in
+ * packets is lrint(ceil(Exp(1 / mean_on_duration))) - or INT_MAX when mean_on_duration <= 0, the "-2" of most shipped
+ * config/*.cfg files.  The flow's end (Rat::_packets_sent == packets_sent_cap_) is found in the transmission phase,
+ * where the idle time to the next flow is drawn from the run's PRNG, in the shuffled sender order.  The cap lives in
+ * SenderCold::pad. */
 
-template <bool COUNT, bool TRACE = false, bool FISH = false>
+template <bool COUNT, bool TRACE = false, bool FISH = false, bool BYTESW = false>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         double *inc_buf, double *hot_send, uint32_t HS, /* per-tick arrays, element i at [i * HS] */
                         double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
@@ -338,6 +344,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         SendState *sendst,                  /* [n_max] mirror of the send fields of `cold` */
                         SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
 {
+  static_assert(!(BYTESW && (FISH || TRACE)), "ByteSwitchedSender is built for Rat senders, without the lookup log");
   const uint32_t pair = A.sim_map ? A.sim_map[sim] : sim;
   const uint32_t cand = pair / A.n_cfgs, cfg_i = pair - cand * A.n_cfgs;
   const RemyNetConfig cfg = A.cfgs[cfg_i];
@@ -348,7 +355,10 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
   const uint32_t n = cfg.num_senders;
   /* (on/off durations: a negative or NaN mean, or both means 0, would keep the switch loop below - and the
    * reference's, src/sendergang.cc:95-105 - from ever ending; on a GPU that hangs the device, so it is refused) */
-  const bool bad_durations = !(cfg.mean_on_duration >= 0) || !(cfg.mean_off_duration >= 0) || !(cfg.mean_on_duration + cfg.mean_off_duration > 0);
+  /* (flows: mean_on is a length in packets, <= 0 = unbounded; an idle time of 0 lets a sender whose flow fits its window
+   * start flow after flow in the same instant - the reference then never leaves that tick) */
+  const bool bad_durations = BYTESW ? !(cfg.mean_off_duration > 0)
+                                    : (!(cfg.mean_on_duration >= 0) || !(cfg.mean_off_duration >= 0) || !(cfg.mean_on_duration + cfg.mean_off_duration > 0));
   if (n == 0 || n > A.n_max || n > REMY_MAX_SENDERS || !(cfg.simulation_ticks > 0) || !(cfg.link_ppt > 0) || bad_durations) {
     res.error = REMY_ERR_BAD_CONFIG;
     A.out_sims[sim] = res;
@@ -579,6 +589,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           double itick = t_old;        /* SwitchedSender::internal_tick of a sender that was on */
           double shr = share[s];
           do {
+            if (BYTESW && sending) { err |= REMY_ERR_ASSERT; break; } /* "never sets a time to switch off" (sendergang.cc:119) */
             if (sending) {             /* switch_off (sendergang.cc:151-161) */
               if (t > itick) { shr = __dadd_rn(shr, __ddiv_rn(__dsub_rn(t, itick), (double)k0)); itick = t; }
               sending = false;
@@ -604,6 +615,14 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
               }
               itick = t;
             }
+            if (BYTESW) { /* ByteSwitchedSender::switcher (sendergang.cc:108-138): no switch-off time; the length of the flow instead */
+              nx = DBL_MAX;
+              const double stop_rate = __ddiv_rn(1.0, cfgp->mean_on_duration);
+              uint32_t flow = 0x7fffffffu; /* numeric_limits<int>::max(): "(almost) infinite flows" */
+              if (stop_rate > 0) flow = (uint32_t)__double2ll_rn(ceil(exp_sample(prng, stop_rate))); /* lrint(ceil(sample)) */
+              if (flow == 0) err |= REMY_ERR_ASSERT; /* assert( new_flow_length > 0 ) */
+              c.pad += flow;
+            } else
             nx = __dadd_rn(nx, exp_sample(prng, __ddiv_rn(1.0, sending ? cfgp->mean_on_duration : cfgp->mean_off_duration)));
           } while (nx <= t);
           nsw[s] = nx;
@@ -823,7 +842,20 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             LinkEnt e; e.tick_sent = t; e.seq = seq; e.src = s;
             lring[ltail & lmask] = e; ltail++;
           }
-          const bool open = (int32_t)(seq + 1) < lim;
+          bool open = (int32_t)(seq + 1) < lim;
+          if (BYTESW && seq + 1 == c->pad) {
+            /* the flow is complete: ByteSwitchedSender::tick (sendergang.cc:270-276) switches the sender off - its sending
+             * time up to this tick is already buffered - and draws the idle time to its next flow */
+            flush_share();
+            const uint32_t bit = 1u << s;
+            on_mask &= ~bit; open = false;
+            if (COUNT) zero_mask &= ~bit;
+            const double nx = __dadd_rn(t, exp_sample(prng, __ddiv_rn(1.0, cfgp->mean_off_duration)));
+            nsw[s] = nx;
+            min_switch = fmin(min_switch, nx);
+            const uint32_t k = __popc(on_mask);
+            if (k) inv_on = __ddiv_rn(1.0, (double)k);
+          }
           const double st = open ? __dadd_rn(t, isend) : DBL_MAX;
           hot_send[s * HS] = st;
           if (!open) open_mask &= ~(1u << s);
@@ -974,7 +1006,7 @@ constexpr size_t SIM_SMEM_MAX = 226 * 1024;
 
 #ifndef REMY_HOST_EMU
 
-template <bool COUNT, bool TRACE = false, bool FISH = false>
+template <bool COUNT, bool TRACE = false, bool FISH = false, bool BYTESW = false>
 __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1012,7 +1044,7 @@ __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_ke
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT, TRACE, FISH>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
+    run_sim<COUNT, TRACE, FISH, BYTESW>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
   }
 }
 

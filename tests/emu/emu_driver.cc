@@ -41,6 +41,17 @@ extern "C" int remy_emu_score_batch_fish(const RemyFlatTree *tree,
   return score_batch_kind(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders, out_use_counts, link_cap_override, 1);
 }
 
+/* Rat senders behind ByteSwitchedSender (flows of a random length in packets) */
+extern "C" int remy_emu_score_batch_flows(const RemyFlatTree *tree,
+                                          const RemyLeafOverride *cands, uint32_t n_cands,
+                                          const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
+                                          uint32_t sender_stride,
+                                          RemySimResult *out_sims, RemySenderResult *out_senders,
+                                          uint32_t *out_use_counts, uint32_t link_cap_override)
+{
+  return score_batch_kind(tree, cands, n_cands, cfgs, seeds, n_cfgs, sender_stride, out_sims, out_senders, out_use_counts, link_cap_override, 2);
+}
+
 static int score_batch_kind(const RemyFlatTree *tree,
                             const RemyLeafOverride *cands, uint32_t n_cands,
                             const RemyNetConfig *cfgs, const uint32_t *seeds, uint32_t n_cfgs,
@@ -75,7 +86,11 @@ static int score_batch_kind(const RemyFlatTree *tree,
     TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
     std::vector<uint32_t> redo;
     for (uint32_t sim : todo) {
-      if (fish) {
+      if (fish == 2) {
+        if (out_use_counts) run_sim<true, false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        else run_sim<false, false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
+      }
+      else if (fish) {
         if (out_use_counts) run_sim<true, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
         else run_sim<false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
       }

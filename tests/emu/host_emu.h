@@ -44,6 +44,7 @@ static inline int32_t __double2int_rz(double v)
 }
 static inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, sizeof r); return r; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline long long __double2ll_rn(double v) { return llrint(v); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 using std::max;
 using std::min;
