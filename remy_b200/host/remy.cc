@@ -491,6 +491,10 @@ FlatTree flatten(const WhiskerTree &root)
 }
 
 /* -------------------------------------------------------------- Evaluator -- */
+static bool g_flow_switched = false;
+void set_flow_switched(bool on) { g_flow_switched = on; }
+bool flow_switched() { return g_flow_switched; }
+
 static uint32_t lcg(uint32_t x) { return (uint32_t)(((uint64_t)x * 16807u) % 2147483647u); }
 
 std::vector<uint32_t> Evaluator<WhiskerTree>::seeds(unsigned int prng_seed, size_t n)
@@ -627,12 +631,13 @@ Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_w
   std::vector<RemySimResult> sims(cfgs.size());
   std::vector<RemySenderResult> snd(cfgs.size() * (size_t)stride);
   std::vector<uint32_t> counts(ft.leaves.size());
+  if (trace && g_flow_switched) throw std::runtime_error("trace == true scoring is not available for flow-switched senders");
   if (trace) { /* Rat(run_whiskers, trace) (src/evaluator.cc:93): every lookup also feeds the leaf's running medians */
     TrackSink sink = make_sink(run_whiskers);
     if (remy_b200_score_trace(&tree, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
                               sims.data(), snd.data(), counts.data(), TrackSink::feed, &sink))
       throw std::runtime_error(std::string("remy_b200_score_trace: ") + remy_b200_last_error());
-  } else if (remy_b200_score_batch(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
+  } else if ((g_flow_switched ? remy_b200_score_batch_flows : remy_b200_score_batch)(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
                             sims.data(), snd.data(), counts.data()))
     throw std::runtime_error(std::string("remy_b200_score_batch: ") + remy_b200_last_error());
   Outcome out;
@@ -744,7 +749,7 @@ std::vector<double> Evaluator<WhiskerTree>::score_candidates(const WhiskerTree &
     cands.push_back(o);
   }
   std::vector<RemySimResult> sims(cands.size() * cfgs.size());
-  if (!cands.empty() && remy_b200_score_batch(&tree, cands.data(), (uint32_t)cands.size(), cfgs.data(), sd.data(), (uint32_t)cfgs.size(), 0,
+  if (!cands.empty() && (g_flow_switched ? remy_b200_score_batch_flows : remy_b200_score_batch)(&tree, cands.data(), (uint32_t)cands.size(), cfgs.data(), sd.data(), (uint32_t)cfgs.size(), 0,
                                               sims.data(), nullptr, nullptr))
     throw std::runtime_error(std::string("remy_b200_score_batch: ") + remy_b200_last_error());
   std::vector<double> scores(cands.size(), 0.0);

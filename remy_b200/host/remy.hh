@@ -245,6 +245,13 @@ public:
   static std::vector<uint32_t> seeds(unsigned int prng_seed, size_t n);
 };
 
+/* Sender switching of every Evaluator<WhiskerTree> of this process: false (default) = TimeSwitchedSender, exponential on
+ * and off TIMES, what the reference's Evaluator builds (src/evaluator.cc:92-93); true = ByteSwitchedSender
+ * (src/sendergang.cc:108-138, 256-278): mean_on_duration is a mean flow length in PACKETS (<= 0: unbounded), which is what
+ * `on` means in the shipped config/*.cfg files.  CLIs: switch=bytes.  trace == true scoring exists for the default only. */
+void set_flow_switched(bool on);
+bool flow_switched();
+
 /* dev= option of the CLIs: "N" binds one CUDA device, "N,M,..." or "all" several - every batch (an
  * evaluator pass, the candidates of an improve step) is then partitioned over them by the library
  * (remy_b200_init_devices), the way the reference spreads an improve step over the cores of one machine

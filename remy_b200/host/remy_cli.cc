@@ -6,7 +6,7 @@
  * SURVEY.md Appendix A).  Every run optimises the whisker actions and then bisects the most used
  * whisker (RatBreeder::improve incl. apply_best_split, see breeder.hh).
  * Extensions: runs=N (stop after N improve() rounds; default: forever, like the reference),
- *             seed=N (default time ^ pid), dev=N | N,M,... | all (several GPUs share every batch).
+ *             seed=N (default time ^ pid), switch=bytes (flow-switched senders, see sender_runner.cc), dev=N | N,M,... | all (several GPUs share every batch).
  */
 #include <cstdio>
 #include <cstdlib>
@@ -82,6 +82,7 @@ int main(int argc, char *argv[])
     } else if (key == "runs=") max_runs = atol(val.c_str());
     else if (key == "seed=") seed = (unsigned int)strtoul(val.c_str(), nullptr, 10);
     else if (key == "dev=") device = val;
+    else if (key == "switch=") remy_b200::set_flow_switched(val == "bytes");
   }
   if (config_filename.empty()) {
     fprintf(stderr, "An input configuration protobuf must be provided via the cf= option. \n");
@@ -92,7 +93,7 @@ int main(int argc, char *argv[])
    * ByteSwitchedSender, -2 meaning unbounded (src/sendergang.cc:128-134).  The Rat path switches senders in time
    * (TimeSwitchedSender): a non-positive "on" would never let the switch loop end, so it is mapped to the
    * sender-runner default of 5000 ms (src/sender-runner.cc:53), like sender_runner.cc does for cf=. */
-  if (options.config_range.mean_on_duration.low <= 0) {
+  if (!remy_b200::flow_switched() && options.config_range.mean_on_duration.low <= 0) {
     fprintf(stderr, "mean_on_duration %f..%f is not a duration (a ByteSwitchedSender flow length?): using 5000 ms\n",
             options.config_range.mean_on_duration.low, options.config_range.mean_on_duration.high);
     options.config_range.mean_on_duration = Range(5000, 5000, 0);

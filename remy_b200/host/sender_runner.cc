@@ -7,7 +7,8 @@
  *   if= nsrc= link= rtt= on= off= buf= sloss=
  * Extensions (the reference has none of these): seed=N (default: time ^ pid, src/random.cc:9),
  *   ticks=N (default 1000000, src/sender-runner.cc:57), cf=FILE (a config/ .cfg ConfigRange[Unicorn]
- *   file, mapped as in SURVEY.md Appendix A: every *.low; on <= 0 -> 5000 ms), dev=N | N,M,... | all (several GPUs share every batch).
+ *   file, mapped as in SURVEY.md Appendix A: every *.low; on <= 0 -> 5000 ms), switch=bytes (ByteSwitchedSender: on= is a
+ *   mean flow length in packets, <= 0 unbounded - the meaning `on` has in the shipped .cfg files), dev=N | N,M,... | all (several GPUs share every batch).
  */
 #include <cmath>
 #include <cstdio>
@@ -133,7 +134,9 @@ int main(int argc, char *argv[])
       const ConfigRange r = ConfigRange::parse(raw.data(), raw.size());
       link_ppt = r.link_ppt.low; delay = r.rtt.low; nsrc_arg = (unsigned int)r.num_senders.low;
       buffer_size = r.buffer_size.low; mean_off_duration = r.mean_off_duration.low;
-      mean_on_duration = r.mean_on_duration.low > 0 ? r.mean_on_duration.low : 5000.0;
+      /* time-switched senders: a non-positive "on" is a ByteSwitchedSender flow length, not a duration -> the
+       * sender-runner default; with switch=bytes (given BEFORE cf=) the file's value is kept: -2 = unbounded flows */
+      mean_on_duration = (r.mean_on_duration.low > 0 || remy_b200::flow_switched()) ? r.mean_on_duration.low : 5000.0;
       stochastic_loss_rate = r.stochastic_loss_rate.low;
       if (r.simulation_ticks) simulation_ticks = r.simulation_ticks;
     } else if (key == "buf=") {
@@ -142,6 +145,8 @@ int main(int argc, char *argv[])
       seed = (unsigned int)strtoul(val.c_str(), nullptr, 10);
     } else if (key == "ticks=") {
       simulation_ticks = (unsigned int)strtoul(val.c_str(), nullptr, 10);
+    } else if (key == "switch=") {
+      remy_b200::set_flow_switched(val == "bytes");
     } else if (key == "dev=") {
       device = val;
     }
