@@ -87,9 +87,15 @@ def improve_step_inputs(args, dev):
     raise SystemExit("no whisker with an optimizable action")
 
 
-def evaluator_pass_inputs(args, rank):
-    tree = workloads.load_golden_tree(args.tree)
+FISH_LAMBDAS, FISH_CUTS = [0.02, 0.01, 0.004], [2.0, 20.0]   # batches of five packets per ms, by rtt_diff (ms)
+
+
+def evaluator_pass_inputs(args, rank, kind="rat"):
+    tree = abi.fin_tree(FISH_LAMBDAS, FISH_CUTS) if kind == "fish" else workloads.load_golden_tree(args.tree)
     base = workloads.default_config_range(ticks=args.ticks)
+    if kind == "flows":
+        base["mean_on_duration"] = 80.0      # mean flow length in packets (the figure4 config files)
+        base["mean_off_duration"] = 500.0
     cfgs = np.tile(base, args.replicas)
     # every (rank, replica) is its own Evaluator seed; seeds within a replica follow seeds_for()
     seeds = np.concatenate([workloads.seeds_for(1000 + rank * args.replicas + r, len(base)) for r in range(args.replicas)])
@@ -171,7 +177,7 @@ def cpu_model():
     return "unknown"
 
 
-def run_cpu(tree, cfgs, seeds, cands=None, shape="pool", repeats=1):
+def run_cpu(tree, cfgs, seeds, cands=None, shape="pool", repeats=1, sender="rat"):
     """Times the reference's own CPU implementation (oracle/_ref) or, if it was not built, the oracle port, on all
     host threads; best of `repeats`.  Returns a dict (value = packet-events/s) and the per-simulation results."""
     from oracle import bindings as checkers  # the CPU baseline leg is the one place bench.py executes oracle/
@@ -186,7 +192,10 @@ def run_cpu(tree, cfgs, seeds, cands=None, shape="pool", repeats=1):
     best, sims = None, None
     for _ in range(max(1, repeats)):
         t0 = time.perf_counter()
-        if shape == "async":
+        if sender != "rat":
+            f = lib.score_fish if sender == "fish" else lib.score_flows
+            sims, _, _ = f(tree, cfgs, seeds, cands=cands, want_senders=False, threads=threads)
+        elif shape == "async":
             sims = lib.score_async_per_candidate(tree, cfgs, seeds, cands=cands)
         else:
             sims, _, _ = lib.score(tree, cfgs, seeds, cands=cands, want_senders=False, threads=threads)
@@ -247,7 +256,9 @@ def main():
     ap.add_argument("--cpu-stride", type=int, default=4, help="CPU leg: every n-th NetConfig of one replica")
     ap.add_argument("--cpu-shape", default="pool", choices=["pool", "async"])
     ap.add_argument("--cpu-repeats", type=int, default=1)
-    ap.add_argument("--workload", default="evaluator-pass", choices=["evaluator-pass", "improve-step", "policy-sweep"])
+    ap.add_argument("--workload", default="evaluator-pass", choices=["evaluator-pass", "improve-step", "policy-sweep", "fish-pass", "flows-pass"],
+                    help="fish-pass: the evaluator pass with Fish senders over a FinTree (Evaluator<FinTree>::score, src/evaluator.cc:105-132); "
+                         "flows-pass: with Rat senders behind ByteSwitchedSender, flows of mean 80 packets (src/sendergang.cc:108-138)")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="improve-step / policy-sweep: strong = ONE batch partitioned over the ranks (default for them); "
                          "weak = every rank its own batch (default for evaluator-pass)")
@@ -256,8 +267,10 @@ def main():
     ap.add_argument("--parity-sample", type=int, default=200, help="simulations the CPU leg re-scores and compares (0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity leg")
     args = ap.parse_args()
+    pass_like = args.workload in ("evaluator-pass", "fish-pass", "flows-pass")
     if args.scaling is None:
-        args.scaling = "weak" if args.workload == "evaluator-pass" else "strong"
+        args.scaling = "weak" if pass_like else "strong"
+    kind = {"fish-pass": "fish", "flows-pass": "flows"}.get(args.workload, "rat")
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -271,7 +284,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        if args.workload != "evaluator-pass":
+        if not pass_like:
             tree = workloads.load_golden_tree(args.tree)
             base = workloads.default_config_range(ticks=args.ticks)
             cands = workloads.candidate_grid(0, base=(2, 0.9, 1.0), n=(os.cpu_count() or 1))
@@ -281,7 +294,7 @@ def main():
                       f"({len(idx)} configs), {args.ticks:g} ticks")
             workload = f"BASELINE configs[2] shape: candidates x NetConfigs of one improve step, {args.ticks:g} ticks (CPU sample)"
         else:
-            tree, cfgs, seeds = evaluator_pass_inputs(args, 0)
+            tree, cfgs, seeds = evaluator_pass_inputs(args, 0, kind)
             n_base = len(cfgs) // args.replicas
             idx = np.arange(0, n_base, args.cpu_stride)
             scfg, sseed, cands = cfgs[idx], seeds[idx], None
@@ -291,10 +304,10 @@ def main():
                         f"{args.ticks:g} ticks")
         config = {"workload": workload, "ticks": args.ticks, "tree": args.tree, "l2": l2_note}
         for _ in range(min(args.warmup, 1)):
-            run_cpu(tree, scfg[:32], sseed[:32], cands, args.cpu_shape)
+            run_cpu(tree, scfg[:32], sseed[:32], cands, args.cpu_shape, 1, kind)
         tot_t, tot_ev, tot_ticks, cpu = 0.0, 0, 0, None
         for _ in range(args.steps):
-            cpu, sims = run_cpu(tree, scfg, sseed, cands, args.cpu_shape)
+            cpu, sims = run_cpu(tree, scfg, sseed, cands, args.cpu_shape, 1, kind)
             tot_t += cpu["seconds"]; tot_ev += int((sims["packets_sent"] + sims["packets_received"]).sum())
             tot_ticks += int(sims["event_ticks"].sum())
         value = tot_ev / tot_t
@@ -330,11 +343,17 @@ def main():
 
     # ---- the rank's batch: (tree, candidates, this rank's configs) ----
     cands, shard, layout, n_cfgs_all = None, None, None, None
-    if args.workload == "evaluator-pass":
-        tree, cfgs, seeds = evaluator_pass_inputs(args, rank)
+    if pass_like:
+        tree, cfgs, seeds = evaluator_pass_inputs(args, rank, kind)
         workload = (f"BASELINE configs[1]: default Remy ConfigRange (800 NetConfigs: link 1-2 ppt x rtt 100-200 ms x nsrc 1-32, "
                     f"exp on/off 5 s, infinite buffer) x {args.replicas} evaluator seeds per GPU, fixed WhiskerTree {args.tree}, "
                     f"{args.ticks:g} ticks")
+        if kind == "fish":
+            workload = (f"Evaluator<FinTree> pass: the default ConfigRange (800 NetConfigs) x {args.replicas} evaluator seeds per GPU, Fish senders, "
+                        f"FinTree lambda {FISH_LAMBDAS} split at rtt_diff {FISH_CUTS}, {args.ticks:g} ticks")
+        elif kind == "flows":
+            workload = (f"default ConfigRange (800 NetConfigs) x {args.replicas} evaluator seeds per GPU, Rat senders behind ByteSwitchedSender "
+                        f"(flows of mean 80 packets, idle 500 ms), WhiskerTree {args.tree}, {args.ticks:g} ticks")
         n_units = 800.0
     else:
         if args.workload == "improve-step":
@@ -363,7 +382,8 @@ def main():
     config = {"workload": workload, "sims_per_gpu": int(n_cands * len(cfgs)), "ticks": args.ticks, "tree": args.tree, "l2": l2_note}
 
     # ---- value: staged API, inputs resident in HBM ----
-    batch = dev.create_batch(tree, cfgs, seeds, cands=cands, want_senders=False, want_use_counts=False)
+    batch = dev.create_batch(tree, cfgs, seeds, cands=cands, want_senders=False, want_use_counts=False, fish=kind == "fish", flows=kind == "flows")
+    one_shot = {"rat": dev.score, "fish": dev.score_fish, "flows": dev.score_flows}[kind]
     for _ in range(args.warmup):
         batch.run(timed=True)
         flush_l2()
@@ -389,11 +409,11 @@ def main():
     # ---- e2e: one-shot C-ABI call, host (pinned) buffers in and out ----
     p_cfgs, k1 = pinned_like(cfgs)
     p_seeds, k2 = pinned_like(seeds)
-    dev.score(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
+    one_shot(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e_sims, _, _ = dev.score(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
+        e_sims, _, _ = one_shot(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
         score = float(e_sims["utility"].sum())  # the step's result, read on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -430,7 +450,7 @@ def main():
     cpu, parity_n, parity_bad = None, 0, []
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         rng = np.random.default_rng(7)
-        if args.workload == "evaluator-pass":
+        if pass_like:
             n_base = len(cfgs) // args.replicas
             kidx = np.arange(0, n_base, args.cpu_stride)
             sample = f"every {args.cpu_stride}th NetConfig of one 800-config replica ({len(kidx)} simulations, {args.ticks:g} ticks each)"
@@ -444,7 +464,7 @@ def main():
                 kidx = kidx[:max(1, args.parity_sample // 8)]
                 scand = cands[csel]
                 sample = f"8 random candidates x {len(kidx)} random NetConfigs of the batch ({args.ticks:g} ticks each)"
-        cpu, c_sims = run_cpu(tree, cfgs[kidx], seeds[kidx], scand, args.cpu_shape, args.cpu_repeats)
+        cpu, c_sims = run_cpu(tree, cfgs[kidx], seeds[kidx], scand, args.cpu_shape, args.cpu_repeats, kind)
         cpu["sample"] = sample
         if args.parity_sample > 0:
             g = sims.reshape(n_cands, len(cfgs))
@@ -466,7 +486,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # measured DRAM traffic of this build's launch on this workload, if a capture of the same build exists
         bh = build_hash()
-        wkey = f"{args.workload}/{args.ticks:g}/{args.replicas if args.workload == 'evaluator-pass' else n_cands}/{args.tree}/{config['sims_per_gpu']}"
+        wkey = f"{args.workload}/{args.ticks:g}/{args.replicas if pass_like else n_cands}/{args.tree}/{config['sims_per_gpu']}"
         log(f"traffic key: {wkey}   build hash: {bh}")
         traffic, counters, tnote = None, None, "no ncu capture of this build and workload under profiles/traffic.json"
         try:
