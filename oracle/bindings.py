@@ -108,6 +108,22 @@ class Reference(_ScoreLib):
         return _score_with(self.lib.remy_ref_score_batch_flows, self.path, tree, cfgs, seeds, cands, want_senders, want_use_counts,
                            [(C.c_uint32, threads)])
 
+    def score_chained(self, tree, cfgs, prng_seed):
+        """The reference's public Evaluator<WhiskerTree>::score on several configs in ONE call (one chained PRNG,
+        src/evaluator.cc:84,92-94) -> (score, tput_delay[n_cfgs, stride, 2], use counts)."""
+        f = self.lib.remy_ref_score_chained
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(FlatTreeC), _PTR, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double), _PTR, _PTR]
+        cfgs = np.ascontiguousarray(cfgs, dtype=net_config_dtype)
+        stride = int(cfgs["num_senders"].max())
+        td = np.zeros((len(cfgs), stride, 2))
+        counts = np.zeros(tree.n_leaves, dtype=np.uint32)
+        score = C.c_double()
+        rc = f(tree.byref(), _ptr(cfgs), len(cfgs), int(prng_seed), stride, C.byref(score), _ptr(td), _ptr(counts))
+        if rc != 0:
+            raise RuntimeError(f"remy_ref_score_chained returned {rc}")
+        return score.value, td, counts
+
     def trace_split(self, tree, cfgs, seeds, generation=0, split=True):
         """The reference's own trace == true scoring (per config, on one tree) and, if `split`, the
         body of Breeder::apply_best_split -> (score, use counts, medians[n_leaves, 6], resulting FlatTree)."""

@@ -250,6 +250,36 @@ extern "C" int remy_ref_score_batch(const RemyFlatTree *tree,
   return 0;
 }
 
+/* The reference's PUBLIC Evaluator<WhiskerTree>::score on SEVERAL configs in one call: one PRNG chained through all of
+ * them (src/evaluator.cc:84,92-94).  cfgs[k].simulation_ticks must all be equal (the call takes one run length).
+ * out_tput_delay: per config, per sender, (normalised throughput, average delay), sender_stride pairs per config. */
+extern "C" int remy_ref_score_chained(const RemyFlatTree *tree, const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t prng_seed,
+                                      uint32_t sender_stride, double *out_score, double *out_tput_delay, uint32_t *out_use_counts)
+{
+  if (!tree || !cfgs || !out_score) return REMY_EINVAL;
+  RemyBuffers::WhiskerTree dna;
+  build_dna(tree, 0, nullptr, &dna);
+  WhiskerTree t(dna);
+  std::vector<NetConfig> configs;
+  for (uint32_t k = 0; k < n_cfgs; k++) configs.push_back(to_netconfig(cfgs[k]));
+  auto outcome = Evaluator<WhiskerTree>::score(t, prng_seed, configs, false, (unsigned int)cfgs[0].simulation_ticks);
+  *out_score = outcome.score;
+  if (out_tput_delay)
+    for (uint32_t k = 0; k < n_cfgs; k++) {
+      const auto &td = outcome.throughputs_delays.at(k).second;
+      for (size_t i = 0; i < td.size() && i < sender_stride; i++) {
+        out_tput_delay[((size_t)k * sender_stride + i) * 2] = td[i].first;
+        out_tput_delay[((size_t)k * sender_stride + i) * 2 + 1] = td[i].second;
+      }
+    }
+  if (out_use_counts) {
+    std::vector<unsigned> counts;
+    collect_counts(outcome.used_actions, counts);
+    for (size_t l = 0; l < counts.size() && l < tree->n_leaves; l++) out_use_counts[l] = counts[l];
+  }
+  return 0;
+}
+
 /* Rat senders behind the reference's ByteSwitchedSender: cfgs[k].mean_on_duration is the mean flow length in packets
  * (<= 0: unbounded flows).  White-box loop only: no public entry point of the reference builds this network. */
 extern "C" int remy_ref_score_batch_flows(const RemyFlatTree *tree,

@@ -414,6 +414,8 @@ int remy_host_apply_best_split(void *h, const void *range_bytes, size_t range_si
     return 0;)
 }
 
+void remy_host_set_chained_prng(int on) { set_chained_prng(on != 0); }
+
 /* Evaluator<WhiskerTree>::seeds: the per-config seeds of one Evaluator (INTEGRATION.md shows the same rule). */
 int remy_host_seeds(unsigned int prng_seed, uint32_t *out, uint32_t n)
 {

@@ -495,6 +495,10 @@ static bool g_flow_switched = false;
 void set_flow_switched(bool on) { g_flow_switched = on; }
 bool flow_switched() { return g_flow_switched; }
 
+static bool g_chained_prng = false;
+void set_chained_prng(bool on) { g_chained_prng = on; }
+bool chained_prng() { return g_chained_prng; }
+
 static uint32_t lcg(uint32_t x) { return (uint32_t)(((uint64_t)x * 16807u) % 2147483647u); }
 
 std::vector<uint32_t> Evaluator<WhiskerTree>::seeds(unsigned int prng_seed, size_t n)
@@ -637,6 +641,18 @@ Evaluator<WhiskerTree>::Outcome Evaluator<WhiskerTree>::score(WhiskerTree &run_w
     if (remy_b200_score_trace(&tree, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
                               sims.data(), snd.data(), counts.data(), TrackSink::feed, &sink))
       throw std::runtime_error(std::string("remy_b200_score_trace: ") + remy_b200_last_error());
+  } else if (g_chained_prng) {
+    /* the reference's one PRNG (src/evaluator.cc:84): config k is seeded with the state config k-1 left behind
+     * (a minstd_rand0 state in [1, 2^31-2] seeds the engine to exactly that state) */
+    uint32_t seed = prng_seed;
+    std::vector<uint32_t> c1(ft.leaves.size());
+    for (size_t k = 0; k < cfgs.size(); k++) {
+      if ((g_flow_switched ? remy_b200_score_batch_flows : remy_b200_score_batch)(&tree, nullptr, 1, &cfgs[k], &seed, 1, stride,
+                                                                                   &sims[k], &snd[k * (size_t)stride], c1.data()))
+        throw std::runtime_error(std::string("remy_b200_score_batch: ") + remy_b200_last_error());
+      for (size_t l = 0; l < c1.size(); l++) counts[l] += c1[l];
+      seed = sims[k].prng_state;
+    }
   } else if ((g_flow_switched ? remy_b200_score_batch_flows : remy_b200_score_batch)(&tree, nullptr, 1, cfgs.data(), sd.data(), (uint32_t)cfgs.size(), stride,
                             sims.data(), snd.data(), counts.data()))
     throw std::runtime_error(std::string("remy_b200_score_batch: ") + remy_b200_last_error());

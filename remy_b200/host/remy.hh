@@ -252,6 +252,14 @@ public:
 void set_flow_switched(bool on);
 bool flow_switched();
 
+/* PRNG chaining of every Evaluator<WhiskerTree> of this process.  false (default): every config of a score() call runs on
+ * its own seed (seeds()), so that all simulations of a batch are independent - the batched evaluator.  true: the reference's
+ * literal behaviour - ONE PRNG handed from config to config (src/evaluator.cc:84,92-94), i.e. config k starts where config
+ * k-1 stopped; a multi-config score() then reproduces the reference's number exactly, at the price of running the configs
+ * one after the other (each on a single GPU thread).  For compatibility checks; candidates are still scored unchained. */
+void set_chained_prng(bool on);
+bool chained_prng();
+
 /* dev= option of the CLIs: "N" binds one CUDA device, "N,M,..." or "all" several - every batch (an
  * evaluator pass, the candidates of an improve step) is then partitioned over them by the library
  * (remy_b200_init_devices), the way the reference spreads an improve step over the cores of one machine

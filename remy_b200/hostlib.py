@@ -72,6 +72,10 @@ class HostLib:
     def err(self):
         return self.lib.remy_host_last_error().decode()
 
+    def set_chained_prng(self, on):
+        """the reference's literal PRNG chaining through the configs of a score() call (remy.hh::set_chained_prng)"""
+        self.lib.remy_host_set_chained_prng(int(bool(on)))
+
     def seeds(self, prng_seed, n):
         """Evaluator<WhiskerTree>::seeds(prng_seed, n) of the C++ host mirror."""
         out = np.zeros(n, dtype=np.uint32)

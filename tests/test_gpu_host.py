@@ -97,6 +97,36 @@ def test_single_config_equals_reference(host, reference):
             assert (counts == ref_counts[0]).all()
 
 
+def test_chained_prng_mode_equals_reference_multi_config_score(host, reference):
+    """The reference chains ONE PRNG through all configs of a score() call (src/evaluator.cc:84,92-94), so its number for
+    a multi-config range depends on the order of the configs.  The batched evaluator gives every config its own seed; the
+    compatibility mode (set_chained_prng) runs the configs one after the other, each seeded with the state its predecessor
+    left behind, and must reproduce the reference's PUBLIC multi-config score: same per-sender throughputs and delays, same
+    use counts, score within 1e-9."""
+    flat = workloads.load_golden_tree("RemyCC-2014-100x")
+    tree = host.tree_from_flat(flat)
+    raw = hostlib.encode_config_range(link=(1.0, 2.0, 0.5), rtt=(100, 150, 50), nsrc=(1, 7, 3), buf=(float(abi.BUFFER_INFINITE),) * 2 + (0,),
+                                      off=(2000, 2000, 0), on=(3000, 3000, 0), ticks=30000)
+    cfgs, _ = host.expand(raw)
+    assert len(cfgs) == 18
+    host.set_chained_prng(True)
+    try:
+        for seed in (7, 31337):
+            score, counts, td = tree.score(raw, seed)
+            want_score, want_td, want_counts = reference.score_chained(flat, cfgs, seed)
+            assert abs(score - want_score) <= 1e-9 * abs(want_score)
+            k = 0
+            for c, cfg in enumerate(cfgs):
+                for s in range(int(cfg["num_senders"])):
+                    assert td[k][0] == want_td[c, s, 0] and td[k][1] == want_td[c, s, 1], (c, s)
+                    k += 1
+            assert (counts == want_counts).all()
+    finally:
+        host.set_chained_prng(False)
+    # and the default (per-config seeds) is a different, order-independent number
+    assert tree.score(raw, 7)[0] != score
+
+
 def _alternatives(value, lo, hi, min_change, max_change, mult, unsigned):
     """OptimizationSetting::alternatives (src/action.hh:62-91)."""
     out = [value]
