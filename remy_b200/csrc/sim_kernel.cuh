@@ -48,14 +48,12 @@
 #include <stdint.h>
 #include <float.h>
 #ifdef REMY_HOST_EMU
-constexpr bool defined_host_emu = true;
 /* tests/emu builds this header with g++ to check the restructured event loop
  * against the oracle on machines without a GPU.  Test infrastructure only: the
  * shipped library is always the nvcc build. */
 #include "host_emu.h"
 #define REMY_NOINLINE __attribute__((noinline))
 #else
-constexpr bool defined_host_emu = false;
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
@@ -338,29 +336,15 @@ constexpr uint32_t FISH_BATCH = 5; /* Fish::_batch_size (src/fish.cc:20) */
  * where the idle time to the next flow is drawn from the run's PRNG, in the shuffled sender order.  The cap lives in
  * SenderCold::pad. */
 
-#ifndef REMY_SOA
-#define REMY_SOA 0
-#endif
-constexpr uint32_t GS = (REMY_SOA && !defined_host_emu) ? 32u : 1u;
-template <class T> struct Strided {
-  T *p;
-  __device__ explicit Strided(T *q) : p(q) {}
-  __device__ T &operator[](uint32_t s) const { return p[s * GS]; }
-};
-
 template <bool COUNT, bool TRACE = false, bool FISH = false, bool BYTESW = false>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
                         double *inc_buf, double *hot_send, uint32_t HS, /* per-tick arrays, element i at [i * HS] */
-                        double *share_,                     /* [n_max] Utility::_tick_share_sending, HBM */
-                        double *nsw_,                       /* [n_max] SwitchedSender::next_switch_tick, HBM */
-                        SendState *sendst_,                 /* [n_max] mirror of the send fields of `cold` */
+                        double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
+                        double *nsw,                        /* [n_max] SwitchedSender::next_switch_tick, HBM */
+                        SendState *sendst,                  /* [n_max] mirror of the send fields of `cold` */
                         SenderCold *cold, LinkEnt *lring, DelayEnt *dring, uint32_t *cnt)
 {
   static_assert(!(BYTESW && (FISH || TRACE)), "ByteSwitchedSender is built for Rat senders, without the lookup log");
-  /* element s of the three small per-sender arrays sits at [s * GS]: GS = 1, or 32 with REMY_SOA (the arrays of the 32 lanes
-   * of a warp interleaved, see the kernel below) */
-  const Strided<double> share(share_), nsw(nsw_);
-  const Strided<SendState> sendst(sendst_);
   const uint32_t pair = A.sim_map ? A.sim_map[sim] : sim;
   const uint32_t cand = pair / A.n_cfgs, cfg_i = pair - cand * A.n_cfgs;
   const RemyNetConfig cfg = A.cfgs[cfg_i];
@@ -1051,18 +1035,9 @@ __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_ke
   }
   const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   SenderCold *cold = A.cold + slot * A.n_max;
-#if REMY_SOA
-  /* struct-of-arrays across the warp: element s of lane l at [warp base + s * 32 + l], so that lanes touching the same
-   * sender index together touch one contiguous run */
-  const size_t wbase = (slot & ~(size_t)31) * A.n_max + (slot & 31);
-  double *share = A.share + wbase;
-  double *nsw = A.nsw + wbase;
-  SendState *sendst = A.sendst + wbase;
-#else
   double *share = A.share + slot * A.n_max;
   double *nsw = A.nsw + slot * A.n_max;
   SendState *sendst = A.sendst + slot * A.n_max;
-#endif
   LinkEnt *lring = A.link_ring + slot * A.link_cap;
   DelayEnt *dring = A.delay_ring + slot * A.delay_cap;
   uint32_t *cnt = COUNT ? A.slot_counts + slot * A.n_leaves : nullptr;
