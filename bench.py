@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--sweep-candidates", type=int, default=1)
     ap.add_argument("--parity-sample", type=int, default=200, help="simulations the CPU leg re-scores and compares (0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (one-shot C-ABI) leg: for the very large sweeps")
+    ap.add_argument("--parity-at-scale", action="store_true", help="N > 1: rank 0 still re-scores a sample of ITS shard on the CPU")
     args = ap.parse_args()
     pass_like = args.workload in ("evaluator-pass", "fish-pass", "flows-pass")
     if args.scaling is None:
@@ -409,17 +411,20 @@ def main():
     # ---- e2e: one-shot C-ABI call, host (pinned) buffers in and out ----
     p_cfgs, k1 = pinned_like(cfgs)
     p_seeds, k2 = pinned_like(seeds)
-    one_shot(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e_sims, _, _ = one_shot(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
-        score = float(e_sims["utility"].sum())  # the step's result, read on the host
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert e_sims.tobytes() == sims.tobytes(), "e2e path and staged path disagree"
     h2d = int(p_cfgs.nbytes + p_seeds.nbytes + tree.nodes.nbytes * 96 // 112 + tree.leaves.nbytes + len(cfgs) * 4)
-    d2h = int(e_sims.nbytes)
+    d2h = int(sims.nbytes)
+    if args.no_e2e:
+        e2e_s, score = float("nan"), float(sims["utility"].sum())
+    else:
+        one_shot(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e_sims, _, _ = one_shot(tree, p_cfgs, p_seeds, cands=cands, want_senders=False)
+            score = float(e_sims["utility"].sum())  # the step's result, read on the host
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        assert e_sims.tobytes() == sims.tobytes(), "e2e path and staged path disagree"
 
     # ---- per-candidate scores: only per-simulation utilities cross NVLink (strong scaling), summed in config order ----
     scores_sha, reduce_ms = None, None
@@ -448,7 +453,7 @@ def main():
 
     # ---- CPU leg on rank 0 (N = 1 only): baseline timing + in-run parity on the same simulations ----
     cpu, parity_n, parity_bad = None, 0, []
-    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+    if rank == 0 and (n_gpus == 1 or args.parity_at_scale) and not args.no_cpu:
         rng = np.random.default_rng(7)
         if pass_like:
             n_base = len(cfgs) // args.replicas
@@ -520,7 +525,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": pk_all * args.steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": ({"value": pk_all * args.steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+                        if not args.no_e2e else None),
                 "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu,
                 "parity_checked": parity_n, "parity_ok": (not parity_bad) if parity_n else None,
                 "event_ticks_per_sec": ticks_all * args.steps / secs, "sims_per_sec": sims_all * args.steps / secs,
