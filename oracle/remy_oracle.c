@@ -8,7 +8,7 @@
  *
  * It restates, literally and without the CUDA kernel's restructuring, what
  *   Evaluator<WhiskerTree>::score(tree, seed, {config}, false, ticks)
- * does in CN-TU/remy for ONE config (reference src/evaluator.cc:77-103): build a
+ * (and its Fish / ByteSwitchedSender variants, `kind`) does in CN-TU/remy for ONE config (reference src/evaluator.cc:77-103): build a
  * Network, run the next-event loop, read the utility.  Every function cites the
  * reference lines it follows.  Arithmetic that lives outside /root/reference
  * (libstdc++ 13 <random>/<algorithm>, glibc 2.39 log) is restated from the
@@ -18,9 +18,11 @@
  * Pinning: the reference holds no bit-exact golden vectors for this path
  * (SURVEY.md §4, §8c), so this restatement is pinned against the reference
  * itself: oracle/build_ref.sh compiles the reference's own sources into
- * oracle/_ref/libremy_ref.so, and tests/test_oracle_vs_ref.py checks that every
- * integer observable and the PRNG end state match and utilities agree bit for
- * bit; tests/golden/ (JSON files) holds vectors generated from that reference build.
+ * oracle/_ref/libremy_ref.so, and tests/test_oracle.py (Rat), tests/test_fish.py (Fish),
+ * tests/test_flows.py (ByteSwitchedSender) and tests/test_trace.py (trace == true) check that
+ * every integer observable and the PRNG end state match and utilities agree bit for bit;
+ * tests/golden/ (JSON files) holds vectors generated from that reference build.
+ * One piece is "parity unpinned": Boost's P^2 median (no Boost in the image).
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile).
  */

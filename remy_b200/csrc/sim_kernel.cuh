@@ -70,6 +70,9 @@ constexpr uint32_t INC_BUF = 16;  /* buffered sending-time increments per simula
 #ifndef REMY_CHAIN
 #define REMY_CHAIN 1 /* chained ticks (see run_sim); 0 = one reference tick per pass of the event loop */
 #endif
+#ifndef REMY_DRING_PF
+#define REMY_DRING_PF 0
+#endif
 #ifndef REMY_SD_REPS
 #define REMY_SD_REPS 2 /* times the transmission + link phases are gone through per pass */
 #endif
@@ -936,6 +939,9 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         }
       }
       prefetch_l2(&cold[m_src]); /* the ack's sender record: read at the top of the next pass */
+#if REMY_DRING_PF
+      if (dtail - ddeliv > REMY_DRING_PF) prefetch_l2(&dring[(ddeliv + REMY_DRING_PF) & dmask]); /* the ring entry read a few deliveries from now */
+#endif
       if (ddeliv != dtail) {
         if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
           const DelayEnt h = dring[(ddeliv + 1) & dmask];

@@ -12,7 +12,9 @@
  *   Evaluator<WhiskerTree>        src/evaluator.hh:14-56, src/evaluator.cc:9-38,77-103,196-201
  *   trace == true scoring         src/memoryrange.cc:8-41,60-66 (track, bisect), src/action.hh:25-33,
  *                                 src/whiskertree.cc:17-30,159-180, on remy_b200_score_trace
- * Not mirrored (out of scope): FinTree.
+ * FinTree / Fin / Evaluator<FinTree> / FishBreeder live in fish.{hh,cc}; RatBreeder and the improvers in breeder.{hh,cc}.
+ * Process-wide switches at the end of this header: flow-switched senders (ByteSwitchedSender), the reference's chained
+ * PRNG, the device list.
  */
 #ifndef REMY_HOST_REMY_HH
 #define REMY_HOST_REMY_HH
