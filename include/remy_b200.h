@@ -223,7 +223,7 @@ int remy_b200_batch_create_fish(const RemyFlatTree *tree,
  * Replaces: Network<SenderGang<Rat, ByteSwitchedSender<Rat>>, ...>::run_simulation - the reference's
  * flow-length sender switch (src/sendergang.cc:108-138, 256-278; src/rat-templates.cc:22-26), which the
  * reference itself instantiates only for its RL sender (src/unicornevaluator.cc:109,140) but which is what
- * `on = -2` / `on = 80` mean in the shipped config/*.cfg files.  A sender is switched on after an
+ * `on = -2` / `on = 80` mean in the shipped .cfg files under config/.  A sender is switched on after an
  * exponential idle time (mean_off_duration, ms) and switches itself off when it has SENT its flow;
  * RemyNetConfig.mean_on_duration is the mean flow length in PACKETS (length = lrint(ceil(Exp(1/mean))));
  * mean_on_duration <= 0 = unbounded flows (INT_MAX packets); mean_off_duration must be > 0 (REMY_ERR_BAD_CONFIG

@@ -335,7 +335,7 @@ constexpr uint32_t FISH_BATCH = 5; /* Fish::_batch_size (src/fish.cc:20) */
 /* BYTESW selects ByteSwitchedSender<Rat> (src/sendergang.cc:108-138, 256-278) instead of TimeSwitchedSender<Rat>: a sender
  * is switched ON after an exponential idle time and switches itself OFF when it has sent its flow, whose length in
  * packets is lrint(ceil(Exp(1 / mean_on_duration))) - or INT_MAX when mean_on_duration <= 0, the "-2" of most shipped
- * config/*.cfg files.  The flow's end (Rat::_packets_sent == packets_sent_cap_) is found in the transmission phase,
+ * .cfg files under config/.  The flow's end (Rat::_packets_sent == packets_sent_cap_) is found in the transmission phase,
  * where the idle time to the next flow is drawn from the run's PRNG, in the shuffled sender order.  The cap lives in
  * SenderCold::pad. */
 

@@ -250,7 +250,7 @@ public:
 /* Sender switching of every Evaluator<WhiskerTree> of this process: false (default) = TimeSwitchedSender, exponential on
  * and off TIMES, what the reference's Evaluator builds (src/evaluator.cc:92-93); true = ByteSwitchedSender
  * (src/sendergang.cc:108-138, 256-278): mean_on_duration is a mean flow length in PACKETS (<= 0: unbounded), which is what
- * `on` means in the shipped config/*.cfg files.  CLIs: switch=bytes.  trace == true scoring exists for the default only. */
+ * `on` means in the shipped .cfg files under config/.  CLIs: switch=bytes.  trace == true scoring exists for the default only. */
 void set_flow_switched(bool on);
 bool flow_switched();
 

@@ -89,7 +89,7 @@ int main(int argc, char *argv[])
     fprintf(stderr, "You can generate one using './configuration'. \n");
     return 1;
   }
-  /* The shipped config/*.cfg files are ConfigRangeUnicorn files whose field 76 is a flow length in packets for
+  /* The shipped .cfg files under config/ are ConfigRangeUnicorn files whose field 76 is a flow length in packets for
    * ByteSwitchedSender, -2 meaning unbounded (src/sendergang.cc:128-134).  The Rat path switches senders in time
    * (TimeSwitchedSender): a non-positive "on" would never let the switch loop end, so it is mapped to the
    * sender-runner default of 5000 ms (src/sender-runner.cc:53), like sender_runner.cc does for cf=. */
