@@ -76,6 +76,9 @@ constexpr uint32_t INC_BUF = 16;  /* buffered sending-time increments per simula
 #ifndef REMY_SD_REPS
 #define REMY_SD_REPS 2 /* times the transmission + link phases are gone through per pass */
 #endif
+#ifndef REMY_SD_UNROLL
+#define REMY_SD_UNROLL 0 /* 1 = both goes as straight-line code (no loop header, at which ptxas drains every scoreboard): measured 1 % slower */
+#endif
 
 struct KernelArgs {
   /* tree (global copies; staged into shared memory when it fits) */
@@ -138,6 +141,55 @@ __device__ __forceinline__ uint32_t warp_max_here(uint32_t v)
 #endif
 }
 
+/* See run_sim: make the value of a freshly loaded register "used" at this point of the program (x + (-0.0)
+ * is x for every x, including both zeros, infinities and NaN payloads). */
+__device__ __forceinline__ double settle(double x)
+{
+#ifdef REMY_HOST_EMU
+  return x;
+#else
+  double y;
+  asm volatile("add.rn.f64 %0, %1, 0d8000000000000000;" : "=d"(y) : "d"(x));
+  return y;
+#endif
+}
+__device__ __forceinline__ bool settle_positive(double x) /* x > 0.0, evaluated HERE */
+{
+#ifdef REMY_HOST_EMU
+  return x > 0.0;
+#else
+  uint32_t r;
+  asm volatile("{ .reg .pred p; setp.gt.f64 p, %1, 0d0000000000000000; selp.u32 %0, 1, 0, p; }" : "=r"(r) : "d"(x));
+  return r != 0;
+#endif
+}
+
+/* The two per-tick arrays of a simulation (buffered sending-time increments, pacing deadlines of the senders)
+ * live in shared memory, element i of this thread at [i * blockDim.x + threadIdx.x].  They are addressed by
+ * their 32-bit shared-window address through ld/st.shared: through C++ pointers the compiler re-derived the
+ * window base at every access (S2UR SR_CgaCtaId + ULEA, a scoreboarded special-register read: nine of them
+ * per pass of the event loop) and kept two 64-bit generic pointers live. */
+struct TickMem {
+#ifdef REMY_HOST_EMU
+  double *p; uint32_t stride;
+  double ld(uint32_t i) const { return p[i * stride]; }
+  void st(uint32_t i, double v) const { p[i * stride] = v; }
+#else
+  uint32_t base; /* shared-window byte address of this thread's element 0 */
+  uint32_t stride; /* bytes between consecutive elements */
+  __device__ __forceinline__ double ld(uint32_t i) const
+  {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + i * stride));
+    return v;
+  }
+  __device__ __forceinline__ void st(uint32_t i, double v) const
+  {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + i * stride), "d"(v));
+  }
+#endif
+};
+
 /* ---------------------------------------------------------------- PRNG ---- */
 /* minstd_rand0 step (bits/random.h:1592, 368-372): 16807 x mod (2^31-1) via the
  * Mersenne fold (2^31 == 1 mod m). */
@@ -167,11 +219,20 @@ __device__ __forceinline__ double canonical(uint32_t &x)
   return ret;
 }
 
-/* Exponential::sample (src/exponential.hh:22; bits/random.h:4898-4905). */
-__device__ REMY_NOINLINE double exp_sample(uint32_t &x, double rate)
+/* Exponential::sample (src/exponential.hh:22; bits/random.h:4898-4905).  The out-of-line part takes the
+ * engine state BY VALUE: a PRNG whose address is passed to a function that is not inlined lives in local
+ * memory for the whole kernel (the event loop then began every pass with a stack load of it and ended every
+ * shuffle with a store); the caller advances the state itself by the two draws of generate_canonical. */
+__device__ REMY_NOINLINE double exp_draw(uint32_t x, double rate)
 {
   const double u = canonical(x);
   return __ddiv_rn(-remy_exact_log(__dsub_rn(1.0, u)), rate);
+}
+__device__ __forceinline__ double exp_sample(uint32_t &x, double rate)
+{
+  const double v = exp_draw(x, rate);
+  x = lcg_mul(x, 282475249u); /* two steps: 16807^2 */
+  return v;
 }
 
 /* uniform_int_distribution{0,u}, fallback branch (bits/uniform_int_dist.h:333-339). */
@@ -341,7 +402,7 @@ constexpr uint32_t FISH_BATCH = 5; /* Fish::_batch_size (src/fish.cc:20) */
 
 template <bool COUNT, bool TRACE = false, bool FISH = false, bool BYTESW = false>
 __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
-                        double *inc_buf, double *hot_send, uint32_t HS, /* per-tick arrays, element i at [i * HS] */
+                        const TickMem tm, /* per-tick arrays: elements [0, INC_BUF) = increments, INC_BUF + s = deadline of sender s */
                         double *share,                      /* [n_max] Utility::_tick_share_sending, HBM */
                         double *nsw,                        /* [n_max] SwitchedSender::next_switch_tick, HBM */
                         SendState *sendst,                  /* [n_max] mirror of the send fields of `cold` */
@@ -403,9 +464,14 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
    * re-read from the config array (a broadcast, cache-resident load) instead of living in registers:
    * the event loop keeps ~60 values live and spills would land in its hottest part. */
   const RemyNetConfig *cfgp = &A.cfgs[cfg_i];
-  const double delay = cfg.delay;
+  /* `delay` and the loss flag are first USED deep inside the event loop.  ptxas tracks a pending load per
+   * register, and all global loads of this kernel share one scoreboard: a first use inside the loop puts a
+   * wait for that scoreboard there on every pass, which in steady state waits for whatever load was issued
+   * last - the link phase's loss test stalled for the send-state prefetch issued just before it.  settle()
+   * is an instruction of its own in front of the loop, so the wait happens here, once. */
+  const double delay = settle(cfg.delay);
   const uint32_t limit = cfg.buffer_size;
-  const bool lossy = cfg.stochastic_loss_rate > 0.0;
+  const bool lossy = settle_positive(cfg.stochastic_loss_rate);
   const double service = __ddiv_rn(1.0, cfg.link_ppt);            /* link.hh:24 */
   const uint32_t lmask = A.link_cap - 1, dmask = A.delay_cap - 1;
 
@@ -424,7 +490,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     cold[s] = c;
     min_switch = fmin(min_switch, first_switch);
     share[s] = 0.0;
-    hot_send[s * HS] = DBL_MAX;
+    tm.st(INC_BUF + s, DBL_MAX);
   }
   if (COUNT) for (uint32_t l = 0; l < A.n_leaves; l++) cnt[l] = 0;
 
@@ -459,7 +525,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
      * interleave in the FP64 pipe.  The increments are read from shared memory once per group; padding up
      * to a multiple of two holds +0.0 (v + 0.0 == v exactly for the non-negative sums kept here). */
     const uint32_t kmax = (ninc + 1u) & ~1u;
-    if (ninc & 1u) inc_buf[ninc * HS] = 0.0;
+    if (ninc & 1u) tm.st(ninc, 0.0);
     uint32_t am = on_mask;
     while (am) {
       const uint32_t s0 = __ffs(am) - 1; am &= am - 1;
@@ -468,7 +534,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       const bool h3 = am != 0; const uint32_t s3 = h3 ? __ffs(am) - 1 : s0; am &= am - 1;
       double v0 = share[s0], v1 = share[s1], v2 = share[s2], v3 = share[s3];
       for (uint32_t k = 0; k < kmax; k += 2) {
-        const double i0 = inc_buf[k * HS], i1 = inc_buf[(k + 1) * HS];
+        const double i0 = tm.ld(k), i1 = tm.ld((k + 1));
         v0 = __dadd_rn(__dadd_rn(v0, i0), i1); v1 = __dadd_rn(__dadd_rn(v1, i0), i1);
         v2 = __dadd_rn(__dadd_rn(v2, i0), i1); v3 = __dadd_rn(__dadd_rn(v3, i0), i1);
       }
@@ -524,7 +590,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     prng_before_shuffle = prng;
     prng = shuffle_skip(prng, n);
     zero_window_lookups(0);
-    if (on_mask) { inc_buf[ninc * HS] = share_of(__dsub_rn(t2, t), (double)__popc(on_mask)); ninc++; }
+    if (on_mask) { tm.st(ninc, share_of(__dsub_rn(t2, t), (double)__popc(on_mask))); ninc++; }
     t = t2;
   };
 
@@ -638,12 +704,12 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             if (itick == t) newly_on |= bit;
             /* (a sender that is on after its switch tick was reset in it: a Fish then sends at once) */
             const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
-            hot_send[s * HS] = FISH ? 0.0 : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
+            tm.st(INC_BUF + s, FISH ? 0.0 : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX));
             open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
             if (COUNT && !FISH) zero_mask = (c.window == 0) ? (zero_mask | bit) : (zero_mask & ~bit);
           } else {
             on_mask &= ~bit; open_mask &= ~bit;
-            hot_send[s * HS] = DBL_MAX;
+            tm.st(INC_BUF + s, DBL_MAX);
             if (COUNT) zero_mask &= ~bit;
           }
         }
@@ -663,7 +729,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       }
     } else if (advanced && on_mask) {
       /* ---- 5. accumulate_sending_time_until, buffered ---- */
-      inc_buf[ninc * HS] = share_of(__dsub_rn(t, t_old), (double)__popc(on_mask));
+      tm.st(ninc, share_of(__dsub_rn(t, t_old), (double)__popc(on_mask)));
       ninc++;
     }
 
@@ -750,7 +816,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
         const uint32_t bit = 1u << s;
         if (on_mask & bit) {
           const bool open = FISH || (int32_t)c.packets_sent < c.largest_ack + 1 + c.window;
-          hot_send[s * HS] = FISH ? fish_due : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX);
+          tm.st(INC_BUF + s, FISH ? fish_due : (open ? __dadd_rn(c.last_send_time, c.intersend) : DBL_MAX));
           open_mask = open ? (open_mask | bit) : (open_mask & ~bit);
           if (COUNT && !FISH) zero_mask = (c.window == 0 || ((reopened >> s) & 1u)) ? (zero_mask | bit) : (zero_mask & ~bit);
         }
@@ -765,7 +831,11 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     /* (the transmission and link phases, with their chain points, can be gone through more than once per
      * pass: between two deliveries a busy link sees one departure and about one transmission, in either
      * order) */
+#if REMY_SD_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int rep = 0; rep < REMY_SD_REPS; rep++) {
     /* ---- chain point S: nothing to transmit in this tick and nothing else due at its time, and the next
      * reference tick starts with a pacing deadline (a departure or delivery at that same time follows in
@@ -787,7 +857,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       uint32_t om = open_mask;
       while (om) {
         const uint32_t s = __ffs(om) - 1; om &= om - 1;
-        const double st = hot_send[s * HS];
+        const double st = tm.ld(INC_BUF + s);
         if (st <= t) ready |= 1u << s; else if (st < ns) { ns = st; ns_sender = s; }
       }
       if (ready) {
@@ -830,7 +900,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             const double st = __dadd_rn(t, __dmul_rn((double)FISH_BATCH, (mx < x) ? mx : x)); /* _update_send_time(tickno) */
             c->packets_sent = seq; c->last_send_time = t; c->intersend = isend; c->window = (int32_t)fp;
             { SendState ss; ss.packets_sent = seq; ss.lim = (int32_t)fp; ss.intersend = isend; sendst[s] = ss; }
-            hot_send[s * HS] = st;
+            tm.st(INC_BUF + s, st);
             if (st < ns) { ns = st; ns_sender = s; }
             continue;
           }
@@ -860,7 +930,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             if (k) inv_on = __ddiv_rn(1.0, (double)k);
           }
           const double st = open ? __dadd_rn(t, isend) : DBL_MAX;
-          hot_send[s * HS] = st;
+          tm.st(INC_BUF + s, st);
           if (!open) open_mask &= ~(1u << s);
           if (st < ns) { ns = st; ns_sender = s; }
         }
@@ -935,7 +1005,13 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             if (rel != t) err |= REMY_ERR_ASSERT;
             ddeliv++;
           }
-          if (ddeliv != dtail) { const DelayEnt h = dring[ddeliv & dmask]; dhead_release = h.release; dh_sent = h.tick_sent; dh_seq = h.seq; dh_src = h.src; }
+          if (ddeliv != dtail) {
+            /* (the loaded fields are used - checked - right here so that the wait for this rare load stays on
+             * this rare path; left to the first use after the join, it made every delivery wait for the ring
+             * read issued below, the one that exists so that nothing has to wait for it) */
+            const DelayEnt h = dring[ddeliv & dmask]; dhead_release = h.release; dh_sent = h.tick_sent; dh_seq = h.seq; dh_src = h.src;
+            if (!(dh_sent <= t) || dh_src >= n || dh_seq == 0xFFFFFFFFu) err |= REMY_ERR_ASSERT;
+          }
         }
       }
       prefetch_l2(&cold[m_src]); /* the ack's sender record: read at the top of the next pass */
@@ -1017,9 +1093,9 @@ __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_ke
 {
   extern __shared__ __align__(16) unsigned char smem[];
   /* layout: [inc_buf: INC_BUF*B doubles][hot_send: n_max*B doubles][tree, if staged] */
-  double *inc_buf = reinterpret_cast<double *>(smem) + threadIdx.x;
-  double *hot_send = inc_buf + (size_t)INC_BUF * blockDim.x;
-  const uint32_t HS = blockDim.x;
+  TickMem tm;
+  tm.base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * (uint32_t)sizeof(double);
+  tm.stride = SIM_BLOCK * (uint32_t)sizeof(double); /* (launched with SIM_BLOCK threads: capi.cu) */
   TreeView T;
   T.axes_mask = A.axes_mask;
   if (A.tree_in_smem) {
@@ -1050,7 +1126,7 @@ __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_ke
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;
-    run_sim<COUNT, TRACE, FISH, BYTESW>(A, T, A.order[w], inc_buf, hot_send, HS, share, nsw, sendst, cold, lring, dring, cnt);
+    run_sim<COUNT, TRACE, FISH, BYTESW>(A, T, A.order[w], tm, share, nsw, sendst, cold, lring, dring, cnt);
   }
 }
 

@@ -87,15 +87,15 @@ static int score_batch_kind(const RemyFlatTree *tree,
     std::vector<uint32_t> redo;
     for (uint32_t sim : todo) {
       if (fish == 2) {
-        if (out_use_counts) run_sim<true, false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
-        else run_sim<false, false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
+        if (out_use_counts) run_sim<true, false, false, true>(A, T, sim, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        else run_sim<false, false, false, true>(A, T, sim, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
       }
       else if (fish) {
-        if (out_use_counts) run_sim<true, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
-        else run_sim<false, false, true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
+        if (out_use_counts) run_sim<true, false, true>(A, T, sim, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        else run_sim<false, false, true>(A, T, sim, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
       }
-      else if (out_use_counts) run_sim<true>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
-      else run_sim<false>(A, T, sim, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
+      else if (out_use_counts) run_sim<true>(A, T, sim, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+      else run_sim<false>(A, T, sim, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), nullptr);
       if (out_sims[sim].error & REMY_ERR_LINK_OVERFLOW) redo.push_back(sim);
     }
     todo.swap(redo);
@@ -154,8 +154,8 @@ static int trace_kind(const RemyFlatTree *tree, const RemyNetConfig *cfgs, const
         A.out_use_counts = phase == 1 ? out_use_counts : scratch_counts.data();
         A.trace_log = phase == 1 ? log : nullptr; A.trace_off = offs.data(); A.out_lookups = out_lookups; A.trace_words = words;
         TreeView T; T.bounds = A.bounds; T.meta = A.meta; T.leaves = A.leaves; T.cuts = A.cuts; T.table = A.table; T.axes_mask = A.axes_mask;
-        if (fish) run_sim<true, true, true>(A, T, k, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
-        else run_sim<true, true>(A, T, k, hot.data(), hot.data() + INC_BUF, 1, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        if (fish) run_sim<true, true, true>(A, T, k, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
+        else run_sim<true, true>(A, T, k, TickMem{hot.data(), 1}, share.data(), nsw.data(), sendst.data(), cold.data(), lring.data(), dring.data(), cnt.data());
         if (!(out_sims[k].error & REMY_ERR_LINK_OVERFLOW) || cap >= (1u << 24)) break;
         cap *= 16;
       }
