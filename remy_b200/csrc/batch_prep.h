@@ -194,7 +194,7 @@ inline BatchPlan plan_batch(const RemyNetConfig *cfgs, uint32_t n_cfgs, uint32_t
     const double bdp = c.link_ppt * c.delay;
     if (c.link_ppt > 0 && c.delay >= 0 && std::isfinite(bdp)) bdp_max = std::max(bdp_max, bdp);
   }
-  p.link_cap = next_pow2(std::max<uint64_t>(any_big ? LINK_CAP_FIRST_TRY : 1, std::max<uint64_t>(lim_max, 1)));
+  p.link_cap = next_pow2(std::max<uint64_t>(any_big ? LINK_CAP_FIRST_TRY : 1, std::max<uint64_t>(lim_max, 1) + 1)); /* (+1: the kernel keeps one ring entry in reserve, sim_kernel.cuh REMY_TOP_LOADS) */
   /* the delay line holds at most floor(delay * link_ppt) + 1 packets in flight plus the
    * delivered-but-unread ones of the current tick */
   p.delay_cap = next_pow2((uint64_t)std::min(bdp_max, 1048000.0) + 8);

@@ -149,13 +149,17 @@ size_t smem_bytes(const DevBatch *b, uint32_t n_max, bool with_tree)
   return (size_t)(INC_BUF + n_max) * SIM_BLOCK * sizeof(double) + (with_tree ? b->tree_bytes : 0);
 }
 
-const void *kernel_fn(const DevBatch *b)
+/* The kernel variants: use counts, lookup log, Fish senders, flow-switched senders - each built twice, for a
+ * tree staged in shared memory (TSM: its reads are ld.shared) and for one read from global memory (a tree
+ * too large for the carve-out). */
+template <bool TSM> const void *kernel_fn_t(const DevBatch *b)
 {
-  if (b->trace) return b->fish ? (const void *)remy_sim_kernel<true, true, true> : (const void *)remy_sim_kernel<true, true>;
-  if (b->fish) return b->want_counts ? (const void *)remy_sim_kernel<true, false, true> : (const void *)remy_sim_kernel<false, false, true>;
-  if (b->flows) return b->want_counts ? (const void *)remy_sim_kernel<true, false, false, true> : (const void *)remy_sim_kernel<false, false, false, true>;
-  return b->want_counts ? (const void *)remy_sim_kernel<true> : (const void *)remy_sim_kernel<false>;
+  if (b->trace) return b->fish ? (const void *)remy_sim_kernel<true, true, true, false, TSM> : (const void *)remy_sim_kernel<true, true, false, false, TSM>;
+  if (b->fish) return b->want_counts ? (const void *)remy_sim_kernel<true, false, true, false, TSM> : (const void *)remy_sim_kernel<false, false, true, false, TSM>;
+  if (b->flows) return b->want_counts ? (const void *)remy_sim_kernel<true, false, false, true, TSM> : (const void *)remy_sim_kernel<false, false, false, true, TSM>;
+  return b->want_counts ? (const void *)remy_sim_kernel<true, false, false, false, TSM> : (const void *)remy_sim_kernel<false, false, false, false, TSM>;
 }
+const void *kernel_fn(const DevBatch *b, bool tree_in_smem) { return tree_in_smem ? kernel_fn_t<true>(b) : kernel_fn_t<false>(b); }
 
 KernelArgs make_args(DevBatch *b, const Scratch &s, bool tree_in_smem, const uint32_t *order, uint32_t n_work, uint32_t *counter)
 {
@@ -218,7 +222,7 @@ int launch_geometry(DevBatch *b, uint32_t n_max, size_t &smem, bool &tree_in_sme
   tree_in_smem = smem_bytes(b, n_max, true) <= (SIM_BLOCK > 128 ? SIM_SMEM_MAX : (size_t)160 * 1024) && b->tree_bytes <= 64 * 1024;
   smem = smem_bytes(b, n_max, tree_in_smem);
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_fn(b), SIM_BLOCK, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_fn(b, tree_in_smem), SIM_BLOCK, smem));
   if (per_sm < 1) return fail(REMY_ECUDA, "kernel does not fit on an SM");
   /* tuning knob: fewer resident blocks shrink the working set (more of it stays in L2) at the
    * price of fewer warps to hide latency with */
@@ -232,14 +236,8 @@ int launch(DevBatch *b, const Scratch &s, size_t smem, bool tree_in_smem, const 
 {
   CU(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
   const KernelArgs a = make_args(b, s, tree_in_smem, order, n_work, counter);
-  if (b->trace && b->fish) remy_sim_kernel<true, true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else if (b->trace) remy_sim_kernel<true, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else if (b->fish && b->want_counts) remy_sim_kernel<true, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else if (b->fish) remy_sim_kernel<false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else if (b->flows && b->want_counts) remy_sim_kernel<true, false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else if (b->flows) remy_sim_kernel<false, false, false, true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else if (b->want_counts) remy_sim_kernel<true><<<grid, SIM_BLOCK, smem, stream>>>(a);
-  else remy_sim_kernel<false><<<grid, SIM_BLOCK, smem, stream>>>(a);
+  void *params[] = {(void *)&a};
+  CU(cudaLaunchKernel(kernel_fn(b, tree_in_smem), dim3(grid), dim3(SIM_BLOCK), params, smem, stream));
   CU(cudaGetLastError());
   b->launches++;
   return 0;
@@ -257,14 +255,14 @@ int bind_device(int device, int count)
   c->device = device; c->sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   /* the kernel stages the tree in shared memory: allow the large carve-out (a per-device attribute) */
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
-  CU(cudaFuncSetAttribute((const void *)remy_sim_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+  {
+    DevBatch probe; /* every variant: walk the selector */
+    for (int v = 0; v < 16; v++) {
+      probe.trace = (v & 8) ? 1 : 0; probe.fish = (v & 4) != 0; probe.flows = (v & 2) != 0; probe.want_counts = (v & 1) != 0;
+      CU(cudaFuncSetAttribute(kernel_fn(&probe, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+      CU(cudaFuncSetAttribute(kernel_fn(&probe, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIM_SMEM_MAX));
+    }
+  }
   g_ctx.push_back(std::move(c));
   return 0;
 }

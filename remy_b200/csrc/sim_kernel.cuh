@@ -76,6 +76,9 @@ constexpr uint32_t INC_BUF = 16;  /* buffered sending-time increments per simula
 #ifndef REMY_SD_REPS
 #define REMY_SD_REPS 2 /* times the transmission + link phases are gone through per pass */
 #endif
+#ifndef REMY_TOP_LOADS
+#define REMY_TOP_LOADS 1 /* ring reads whose data is needed a pass later are ISSUED at the top of that pass (see run_sim) */
+#endif
 #ifndef REMY_SD_UNROLL
 #define REMY_SD_UNROLL 0 /* 1 = both goes as straight-line code (no loop header, at which ptxas drains every scoreboard): measured 1 % slower */
 #endif
@@ -392,6 +395,7 @@ __device__ __forceinline__ int32_t whisker_window(int32_t prev, double mult, int
  * `intersend` holds Fish::_lambda (0 = not looked up since the reset), `window` the state of
  * Fish::_prng, the pacing deadline (Fish::_next_send_time, 0 = at once) lives in hot_send[];
  * SendState mirrors {packets_sent, prng, lambda}. */
+constexpr uint32_t PEND_STALE = 0xFFFFFFFFu; /* pend_src: the packet in service has not been read from the link ring yet */
 constexpr uint32_t FISH_BATCH = 5; /* Fish::_batch_size (src/fish.cc:20) */
 /* BYTESW selects ByteSwitchedSender<Rat> (src/sendergang.cc:108-138, 256-278) instead of TimeSwitchedSender<Rat>: a sender
  * is switched ON after an exponential idle time and switches itself OFF when it has sent its flow, whose length in
@@ -519,6 +523,8 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
    * and the increment of a switch tick itself is applied at once). */
   uint32_t ninc = 0;
   double inv_on = 0; /* correctly rounded 1 / (number of senders that are on) */
+  double k_on = 0;   /* that number itself, as a double: it only changes at switches, and POPC + I2F.F64 in front of
+                      * every tick's increment were two scoreboarded operations on the path of all lanes */
   auto flush_share = [&]() {
     /* Four senders at a time: their sums are requested together (one memory latency per group instead of
      * one per sender), and the four addition chains - each strictly in order, as the reference adds -
@@ -590,7 +596,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     prng_before_shuffle = prng;
     prng = shuffle_skip(prng, n);
     zero_window_lookups(0);
-    if (on_mask) { tm.st(ninc, share_of(__dsub_rn(t2, t), (double)__popc(on_mask))); ninc++; }
+    if (on_mask) { tm.st(ninc, share_of(__dsub_rn(t2, t), k_on)); ninc++; }
     t = t2;
   };
 
@@ -719,7 +725,8 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       /* ---- 5. accumulate_sending_time_until (sendergang.cc:163-173) of a switch tick: applied at once to the
        * senders that were on before it and still are (nothing is buffered here: ninc == 0) ---- */
       const uint32_t k1 = __popc(on_mask);
-      if (k1) inv_on = __ddiv_rn(1.0, (double)k1);
+      k_on = (double)k1;
+      if (k1) inv_on = __ddiv_rn(1.0, k_on);
       if (advanced) {
         uint32_t am = on_mask & ~newly_on;
         if (am) {
@@ -729,9 +736,26 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       }
     } else if (advanced && on_mask) {
       /* ---- 5. accumulate_sending_time_until, buffered ---- */
-      tm.st(ninc, share_of(__dsub_rn(t, t_old), (double)__popc(on_mask)));
+      tm.st(ninc, share_of(__dsub_rn(t, t_old), k_on));
       ninc++;
     }
+
+#if REMY_TOP_LOADS
+    /* The two ring reads that the previous pass left to this one - the delay-line entry behind the new head,
+     * and the packet that moved from the link's queue into service - are issued here, in front of the shuffle's
+     * chain of LCG steps (which needs no memory).  Their data is not needed
+     * before this pass's delivery / departure; issued where they arose - at the END of the previous pass - they
+     * were waited for at whatever scoreboard wait came next, usually at once (ptxas drains the scoreboards at the
+     * loop header when it finds loads in flight across the back edge). */
+    if (dn_release < 0.0) {
+      const DelayEnt h = dring[(ddeliv + 1) & dmask];
+      dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
+    }
+    if (pend_src == PEND_STALE) {
+      const LinkEnt e = lring[(lhead - 1) & lmask];
+      pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
+    }
+#endif
 
     /* ---- 2. run_senders: the shuffle's PRNG draws (sendergang.cc:75-82) ---- */
     prng_before_shuffle = prng;
@@ -889,7 +913,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
               if (!pending) {
                 pending = true; pend_release = __dadd_rn(t, service); pend_sent = t; pend_seq = seq; pend_src = s;
               } else if ((ltail - lhead) < limit) {
-                if (ltail - lhead >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
+                if (ltail - lhead + REMY_TOP_LOADS >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
                 LinkEnt e; e.tick_sent = t; e.seq = seq; e.src = s;
                 lring[ltail & lmask] = e; ltail++;
               }
@@ -911,7 +935,7 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
           if (!pending) {
             pending = true; pend_release = __dadd_rn(t, service); pend_sent = t; pend_seq = seq; pend_src = s;
           } else if ((ltail - lhead) < limit) { /* (a limit of 0 accepts nothing) */
-            if (ltail - lhead >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
+            if (ltail - lhead + REMY_TOP_LOADS >= A.link_cap) { err |= REMY_ERR_LINK_OVERFLOW; break; }
             LinkEnt e; e.tick_sent = t; e.seq = seq; e.src = s;
             lring[ltail & lmask] = e; ltail++;
           }
@@ -927,7 +951,8 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
             nsw[s] = nx;
             min_switch = fmin(min_switch, nx);
             const uint32_t k = __popc(on_mask);
-            if (k) inv_on = __ddiv_rn(1.0, (double)k);
+            k_on = (double)k;
+            if (k) inv_on = __ddiv_rn(1.0, k_on);
           }
           const double st = open ? __dadd_rn(t, isend) : DBL_MAX;
           tm.st(INC_BUF + s, st);
@@ -957,6 +982,12 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
     /* ---- 6. Link::tick (link-templates.cc:7-18) -> StochasticLoss (stochastic-loss.hh:21-35) -> Delay::accept ---- */
     if (pending && pend_release <= t) {
       if (pend_release != t) err |= REMY_ERR_ASSERT;
+#if REMY_TOP_LOADS
+      if (pend_src == PEND_STALE) { /* (rare: it entered service in this very pass) */
+        const LinkEnt e = lring[(lhead - 1) & lmask];
+        pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
+      }
+#endif
       bool lost;
       if (lossy) lost = canonical(prng) < cfgp->stochastic_loss_rate; /* bernoulli (bits/random.h:3739-3750) */
       else { prng = lcg_mul(prng, 282475249u); lost = false; } /* two draws, 16807^2 */
@@ -976,8 +1007,13 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
       pending = false;
     }
     if (!pending && lhead != ltail) {
+#if REMY_TOP_LOADS
+      lhead++; /* (its slot stays untouched until it has been read: the ring keeps one entry in reserve) */
+      pending = true; pend_release = __dadd_rn(t, service); pend_src = PEND_STALE;
+#else
       const LinkEnt e = lring[lhead & lmask]; lhead++;
       pending = true; pend_release = __dadd_rn(t, service); pend_sent = e.tick_sent; pend_seq = e.seq; pend_src = e.src;
+#endif
     }
     } /* rep */
 
@@ -1018,12 +1054,16 @@ __device__ void run_sim(const KernelArgs &A, const TreeView &T, uint32_t sim,
 #if REMY_DRING_PF
       if (dtail - ddeliv > REMY_DRING_PF) prefetch_l2(&dring[(ddeliv + REMY_DRING_PF) & dmask]); /* the ring entry read a few deliveries from now */
 #endif
+#if REMY_TOP_LOADS
+      if (dtail - ddeliv >= 2) dn_release = -1.0; /* the new second entry: read at the top of the next pass (release times are >= 0) */
+#else
       if (ddeliv != dtail) {
         if (dtail - ddeliv >= 2) { /* read the new second entry now; it is not used before the next delivery */
           const DelayEnt h = dring[(ddeliv + 1) & dmask];
           dn_release = h.release; dn_sent = h.tick_sent; dn_seq = h.seq; dn_src = h.src;
         }
       }
+#endif
     }
   }
 
@@ -1088,7 +1128,10 @@ constexpr size_t SIM_SMEM_MAX = 226 * 1024;
 
 #ifndef REMY_HOST_EMU
 
-template <bool COUNT, bool TRACE = false, bool FISH = false, bool BYTESW = false>
+/* TSM: the tree is staged in shared memory.  A template parameter and not a branch, so that the tree's
+ * pointers are shared-memory pointers at compile time and its reads ld.shared (with a run-time choice they were
+ * generic loads, which ptxas tracks on the same scoreboard as the global loads of the sender records). */
+template <bool COUNT, bool TRACE = false, bool FISH = false, bool BYTESW = false, bool TSM = true>
 __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_kernel(const KernelArgs A)
 {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1098,8 +1141,8 @@ __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_ke
   tm.stride = SIM_BLOCK * (uint32_t)sizeof(double); /* (launched with SIM_BLOCK threads: capi.cu) */
   TreeView T;
   T.axes_mask = A.axes_mask;
-  if (A.tree_in_smem) {
-    unsigned char *p = smem + (size_t)(INC_BUF + A.n_max) * blockDim.x * sizeof(double);
+  if (TSM) {
+    unsigned char *p = smem + (size_t)(INC_BUF + A.n_max) * SIM_BLOCK * sizeof(double);
     Bounds *sb = reinterpret_cast<Bounds *>(p);
     DevLeaf *sl = reinterpret_cast<DevLeaf *>(sb + (size_t)A.n_nodes * NAX);
     DevNodeMeta *sm = reinterpret_cast<DevNodeMeta *>(sl + A.n_leaves);
