@@ -193,3 +193,39 @@ extern "C" uint64_t remy_emu_check_small_div(uint64_t n, uint64_t seed)
   }
   return bad;
 }
+
+/* shuffle_skip (the kernel's advance of the PRNG by std::shuffle's draws without building the permutation)
+ * against the draw-by-draw uniform_int loop: n_random states per sender count, plus states constructed so
+ * that one draw lands among the values uniform_int can reject or among the small residues (where the lazily
+ * reduced fast paths must notice that they cannot be trusted).  Returns the number of mismatches. */
+extern "C" uint64_t remy_emu_check_shuffle_skip(uint64_t n_random, uint64_t seed)
+{
+  using namespace remy;
+  auto exact = [](uint32_t x, uint32_t n) {
+    uint32_t i = 1;
+    if ((n & 1u) == 0) { (void)uniform_int(x, 1); i = 2; }
+    for (; i < n; i += 2) (void)uniform_int(x, (i + 1) * (i + 2) - 1);
+    return x;
+  };
+  auto modpow = [](uint64_t b, uint64_t e) { uint64_t r = 1; const uint64_t m = 2147483647ull; b %= m; while (e) { if (e & 1) r = r * b % m; b = b * b % m; e >>= 1; } return r; };
+  uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+  auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  for (uint32_t n = 1; n <= REMY_MAX_SENDERS; n++) {
+    for (uint64_t k = 0; k < n_random; k++) {
+      const uint32_t x = (uint32_t)(next() % 2147483646ull) + 1;
+      if (shuffle_skip(x, n) != exact(x, n)) bad++;
+    }
+    for (uint32_t j = 1; j <= (n >> 1); j++) {
+      const uint64_t inv = modpow(modpow(16807, j), 2147483647ull - 2); /* 16807^-j mod m */
+      for (uint32_t v = 1; v <= 1300; v++) { /* draw j = m - v */
+        const uint32_t x = (uint32_t)((uint64_t)(2147483647u - v) * inv % 2147483647ull);
+        if (x && shuffle_skip(x, n) != exact(x, n)) bad++;
+      }
+      for (uint32_t v = 1; v <= 40000; v += 7) { /* draw j = v */
+        const uint32_t x = (uint32_t)((uint64_t)v * inv % 2147483647ull);
+        if (x && shuffle_skip(x, n) != exact(x, n)) bad++;
+      }
+    }
+  }
+  return bad;
+}

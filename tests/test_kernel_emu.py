@@ -195,3 +195,13 @@ def test_small_divisor_division(built):
     lib.remy_emu_check_small_div.restype = C.c_uint64
     lib.remy_emu_check_small_div.argtypes = [C.c_uint64, C.c_uint64]
     assert lib.remy_emu_check_small_div(3_200_000, 1) == 0
+
+
+def test_shuffle_skip_is_the_draw_by_draw_loop(built):
+    """sim_kernel.cuh::shuffle_skip advances the run's PRNG by std::shuffle's draws (bits/stl_algo.h:3742-3805,
+    src/sendergang.cc:75-82) on a lazily reduced residue; it must leave exactly the state the uniform_int loop
+    leaves, including for the states where a draw is rejected or the lazy reduction wraps."""
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libremy_emu.so"))
+    lib.remy_emu_check_shuffle_skip.restype = C.c_uint64
+    lib.remy_emu_check_shuffle_skip.argtypes = [C.c_uint64, C.c_uint64]
+    assert lib.remy_emu_check_shuffle_skip(200_000, 3) == 0
