@@ -205,3 +205,24 @@ def test_shuffle_skip_is_the_draw_by_draw_loop(built):
     lib.remy_emu_check_shuffle_skip.restype = C.c_uint64
     lib.remy_emu_check_shuffle_skip.argtypes = [C.c_uint64, C.c_uint64]
     assert lib.remy_emu_check_shuffle_skip(200_000, 3) == 0
+
+
+def test_emu_full_queues_at_ring_boundaries(emu, oracle):
+    """The packet that enters service is read from its ring slot only at the top of the next pass of the event
+    loop (sim_kernel.cuh, REMY_TOP_LOADS), so the ring keeps one entry in reserve.  Finite buffers around the
+    powers of two, kept FULL by bursting senders, and forced ring sizes from 2 entries up must all give the
+    reference's result: no slot is overwritten before it is read."""
+    tree = abi.default_tree()
+    rows = [dict(link_ppt=p, delay=d, num_senders=n, buffer_size=b, mean_on_duration=200, mean_off_duration=10,
+                 simulation_ticks=1200)
+            for p in (0.5, 3.0) for d in (0, 20) for n in (4, 16) for b in (1, 2, 3, 4, 7, 8, 15, 16, 17, 31, 32, 33, 63, 64)]
+    cfgs = abi.make_configs(rows)
+    seeds = np.arange(len(rows), dtype=np.uint32) * 3 + 11
+    cands = np.zeros(2, dtype=abi.leaf_override_dtype)
+    cands[0] = (1.0, 0.0, 40, 0)    # the window grows by 40 per ack, no pacing: the queue is at its limit all the time
+    cands[1] = (0.9, 0.05, 9, 0)
+    want = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=4)
+    full = want[0]["link_queued"].reshape(2, -1)[0] >= np.minimum(cfgs["buffer_size"], 10 ** 9)
+    assert full.mean() > 0.5, "the queues were meant to be full at the end of most runs"
+    for cap in (0, 2, 16, 32):
+        assert_same_results(emu.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, link_cap=cap), want, what=f"link_cap {cap}")
