@@ -138,6 +138,35 @@ def test_p2_median_restatements_agree(host, oracle):
             assert abs(got - np.median(x)) < 0.05 * (np.std(x) + 1e-9)
 
 
+def test_p2_median_reproduces_the_published_worked_example(host, oracle):
+    """Known-answer test from the paper that defines the estimator (Jain & Chlamtac, "The P^2 algorithm for
+    dynamic calculation of quantiles and histograms without storing observations", CACM 28(10), 1985, Table I):
+    twenty observations, p = 0.5, final marker heights 0.02, 0.49, 4.44, 17.20, 38.62 - the paper's estimate
+    of the median is 4.44.  (The per-observation values of the median marker below are this restatement's,
+    rounded like the table's column; they are kept as a regression record.)  Boost's p_square_quantile_impl
+    (what src/memoryrange.hh:24-26 instantiates) is that algorithm; Boost itself is not in the image, so this
+    pins the restatements to the published vector, not to Boost's code."""
+    obs = [0.02, 0.15, 0.74, 3.39, 0.83, 22.37, 10.15, 15.43, 38.62, 15.92,
+           34.60, 10.28, 1.47, 0.40, 0.05, 11.39, 0.27, 0.42, 0.09, 11.37]
+    table = {5: 0.74, 6: 0.74, 7: 0.74, 8: 2.18, 9: 4.75, 10: 4.75, 11: 9.27, 12: 9.27, 13: 9.27, 14: 9.27,
+             15: 6.30, 16: 6.30, 17: 6.30, 18: 6.30, 19: 4.44, 20: 4.44}
+    L = oracle.lib
+    L.remy_oracle_p2_sizeof.restype = C.c_size_t
+    L.remy_oracle_p2_median.restype = C.c_double
+    L.remy_oracle_p2_median.argtypes = [C.c_void_p]
+    L.remy_oracle_p2_init.argtypes = [C.c_void_p]
+    L.remy_oracle_p2_add.argtypes = [C.c_void_p, C.c_double]
+    acc = np.zeros(L.remy_oracle_p2_sizeof(), dtype=np.uint8)
+    L.remy_oracle_p2_init(acc.ctypes.data)
+    for i, v in enumerate(obs, 1):
+        L.remy_oracle_p2_add(acc.ctypes.data, v)
+        if i in table:
+            assert abs(L.remy_oracle_p2_median(acc.ctypes.data) - table[i]) < 0.006, (i, L.remy_oracle_p2_median(acc.ctypes.data))
+            assert abs(host.p2_median(np.array(obs[:i])) - table[i]) < 0.006, i
+    heights = acc.view(np.float64)[:5]
+    assert np.allclose(heights, [0.02, 0.49, 4.44, 17.20, 38.62], atol=0.006), heights
+
+
 @pytest.mark.parametrize("name,tree", trees()[:3])
 def test_host_split_equals_reference(host, oracle, reference, name, tree):
     """Breeder::apply_best_split's body on the host mirror == the reference's own classes: the tree
