@@ -114,6 +114,7 @@ struct KernelArgs {
   const uint32_t *sim_map;       /* nullptr, or [n_sims]: the (candidate, config) index each local simulation id stands for
                                   * (a batch partitioned over several devices: ids, work list and outputs are per device) */
   uint32_t n_cfgs, n_work;
+  uint32_t lanes_per_warp;       /* 32, or fewer: only that many lanes of every warp take work (capi.cu, spread lists) */
   uint32_t *work_counter;
   /* per-slot scratch */
   SenderCold *cold;   uint32_t n_max;      /* [slots][n_max] */
@@ -1207,6 +1208,9 @@ __global__ void __launch_bounds__(SIM_BLOCK, REMY_MIN_BLOCKS_PER_SM) remy_sim_ke
   LinkEnt *lring = A.link_ring + slot * A.link_cap;
   DelayEnt *dring = A.delay_ring + slot * A.delay_cap;
   uint32_t *cnt = COUNT ? A.slot_counts + slot * A.n_leaves : nullptr;
+  /* (a batch with fewer simulations than resident threads is spread over all warps, see capi.cu: the lanes
+   * beyond lanes_per_warp stay idle, so that a warp executes the union of FEWER simulations' code paths) */
+  if ((threadIdx.x & 31u) >= A.lanes_per_warp) return;
   for (;;) {
     const uint32_t w = atomicAdd(A.work_counter, 1u);
     if (w >= A.n_work) break;

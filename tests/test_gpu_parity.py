@@ -51,6 +51,25 @@ def test_gpu_simultaneous_sends_and_ring_regrowth(device, oracle):
     assert_same_results(got, want, exact_utility=False, what="burst")
 
 
+def test_gpu_spread_and_packed_work_lists_agree(device, oracle, monkeypatch):
+    """A batch with fewer simulations than resident threads is spread over all warps (capi.cu: only some lanes
+    of a warp take work, cost strata interleaved); REMY_B200_NO_SPREAD=1 packs it into full warps like a batch
+    that fills the GPU.  Which simulations share a warp must not show in any result."""
+    rng = np.random.default_rng(77)
+    tree = workloads.load_golden_tree("RemyCC-2014-100x")
+    cfgs = random_configs(rng, 150, max_ticks=1e4)
+    seeds = rng.integers(0, 2 ** 32, size=len(cfgs), dtype=np.uint64).astype(np.uint32)
+    cands = random_candidates(rng, tree, 3)
+    want = oracle.score(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=16)
+    spread = device.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    monkeypatch.setenv("REMY_B200_NO_SPREAD", "1")
+    packed = device.score(tree, cfgs, seeds, cands=cands, want_use_counts=True)
+    monkeypatch.delenv("REMY_B200_NO_SPREAD")
+    assert_same_results(spread, want, exact_utility=False, what="spread")
+    assert_same_results(packed, want, exact_utility=False, what="packed")
+    assert_same_results(spread, packed, exact_utility=True, what="spread vs packed")
+
+
 def test_gpu_coincident_events(device, oracle):
     """Timer sends, departures and deliveries on the same instants (see tests/test_kernel_emu.py)."""
     from test_kernel_emu import coincident_event_batch
