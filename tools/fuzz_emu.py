@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Randomised hunt for divergences between the kernel source (CPU build, tests/emu) and the oracle:
 random trees (regular, irregular, bisected, FinTrees), random NetConfigs incl. the reference's edge cases,
-random candidates, both sender families, with and without the lookup log.  Not part of the test suite
+random candidates, both sender families and flow-switched Rat senders, with and without the lookup log.  Not part of the test suite
 (minutes to hours of CPU); prints the first mismatch with everything needed to replay it.
 usage: fuzz_emu.py [seconds] [seed]"""
 import ctypes as C
@@ -42,6 +42,7 @@ while time.time() < t_end:
         else:
             tree = helpers.random_tree(rng, n_children=int(rng.integers(2, 8)), depth=int(rng.integers(1, 4)), grid=(kind == 2),
                                        axes_mask=int(rng.choice([0b1111, 0b1111, 0b110111, 0b0101])))
+    flows = False
     n = int(rng.integers(4, 24))
     cfgs = helpers.random_configs(rng, n, max_ticks=float(rng.choice([2000, 8000, 20000])))
     if rng.integers(0, 4) == 0:   # coincident events: round service times and pacing
@@ -56,6 +57,13 @@ while time.time() < t_end:
             cands[c] = (0, float(rng.choice([0.01, 0.25, 2.0, 29.99])), 0, int(rng.integers(0, tree.n_leaves)))
         a = abi._score_with(emu.remy_emu_score_batch_fish, "emu", tree, cfgs, seeds, cands, True, True, [(C.c_uint32, int(rng.choice([0, 0, 16])))])
         b = orc.score_fish(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=8)
+    elif rng.integers(0, 4) == 0:   # flow-switched Rat senders (ByteSwitchedSender, src/sendergang.cc:108-138,256-278)
+        flows = True
+        cfgs["mean_on_duration"] = rng.choice([-2.0, 0.4, 1.0, 5.0, 80.0, 80.0, 700.0], n)      # mean flow length in packets
+        cfgs["mean_off_duration"] = rng.choice([2.0, 20.0, 500.0, 500.0, 3000.0], n)
+        cands = helpers.random_candidates(rng, tree, ncand)
+        a = abi._score_with(emu.remy_emu_score_batch_flows, "emu", tree, cfgs, seeds, cands, True, True, [(C.c_uint32, int(rng.choice([0, 0, 16])))])
+        b = orc.score_flows(tree, cfgs, seeds, cands=cands, want_use_counts=True, threads=8)
     else:
         cands = helpers.random_candidates(rng, tree, ncand)
         if rng.integers(0, 6) == 0:   # negative / overflowing window multiples (trees from files are not confined to [0, 1])
@@ -76,7 +84,7 @@ while time.time() < t_end:
     try:
         helpers.assert_same_results(a, b, what=f"iteration {it}")
         ok = (a[0]["error"][:n] == 0)
-        if ok.all() and rng.integers(0, 2) == 0:   # the lookup log of the base tree
+        if ok.all() and not flows and rng.integers(0, 2) == 0:   # the lookup log of the base tree
             sims = np.zeros(n, dtype=abi.sim_result_dtype)
             counts = np.zeros(tree.n_leaves, dtype=np.uint32)
             cap = int(a[2][0].sum()) + 16
@@ -101,7 +109,7 @@ while time.time() < t_end:
                 assert rec[:, 1:].tobytes() == np.ascontiguousarray(mem[:, axes]).tobytes(), ("trace values", k2)
                 off += len(leaf)
     except AssertionError as e:
-        print("MISMATCH at iteration", it, "seed0", seed0, "fish", fish, e)
+        print("MISMATCH at iteration", it, "seed0", seed0, "fish", fish, "flows", flows, e)
         sys.exit(1)
     it += 1
     sims_done += len(a[0])
